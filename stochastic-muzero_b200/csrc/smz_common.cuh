@@ -1,0 +1,101 @@
+// smz_common.cuh — shared device/host definitions of the search engine (sm_100a).
+//
+// Arena ("structure of arrays" of vectorised columns, one slice per tree):
+//   stat [B][M] int4   {visit_count i32, value_sum f32, reward f32, prior f32}   Node, mcts.py:6-21
+//   link [B][M] int2   {child_base i32 (0 = not expanded), key i32}
+//   root_prior [B][A] f64   priors of the root children after Dirichlet mixing (f64 in the reference)
+//   minmax [B] float2  MinMaxStats, mcts.py:24-36
+//   hidden [N+1][B][Sp] f32  hidden state of every expanded node: slot 0 = root, slot s+1 = sim s
+// Node 0 is the root, 1..A its children, simulation s allocates its children at 1 + A + s*Kmax, so a
+// node's child_base also names the hidden slot of the node (no allocator, no counters).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SMZ_BRANCH_AFTERSTATE 0
+#define SMZ_BRANCH_DYNAMICS 1
+#define SMZ_MAX_POLICY 32   // widest policy head handled by the lane-per-entry tree kernels
+#define SMZ_HP 128          // padded hidden width of the MLP tiles
+#define SMZ_SP 64           // padded state width
+
+struct SmzArena {
+  // shape
+  int B, N, A, C, K, Kd, Kc, Kmax, M, W, Sp, path_stride, n_phases;
+  // tree columns
+  int4* stat;
+  int2* link;
+  double* root_prior;
+  float2* minmax;
+  int* ucursor;
+  int* root_to_play;
+  // per-simulation scratch
+  int* path;        // [B][path_stride] node indices root..leaf
+  int* path_len;    // [B]
+  int* leaf_node;   // [B]
+  int* leaf_slot;   // [B] hidden slot of search_path[-2]
+  int* leaf_action; // [B] history[-1]
+  int* leaf_branch; // [B]
+  int* branch_count; // [N+1][2] rows per branch of each simulation
+  int* rows;        // [2][B] compacted tree ids per branch
+  int* error_flag;  // [1]
+  unsigned long long* depth_sum;  // [1] sum of leaf depths (bench bookkeeping)
+  // network I/O
+  float* out_policy;  // [B][W]
+  float* out_value;   // [B]
+  float* out_reward;  // [B]
+  float* hidden;      // [N+1][B][Sp]
+  double* dirichlet;  // [B][A]
+  // record
+  float* rec_policy;  // [B][N][W] or null
+  float* rec_value;   // [B][N]
+  float* rec_reward;  // [B][N]
+  signed char* rec_branch;  // [B][N]
+  float* rec_root_policy;   // [B][W]
+  // rng
+  int rng_mode;
+  const double* tape_u;
+  int tape_stride;
+  const unsigned long long* seed_state;  // device [2]: {Philox key, global id of local tree 0}
+  // constants
+  const double* pbc;         // [N+2]
+  const signed char* sign;   // [n_phases][N+2]
+  float discount;
+  float one_minus_frac_f32;  // f32(1 - frac), the weak-scalar cast the reference performs
+  double frac;
+  double alpha;
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (index>>1, stream, tree_lo, tree_hi), key = (seed_lo, seed_hi)
+// (restated on the CPU in oracle/mcts_oracle.py::philox_uniform and oracle/c/smz_oracle.c)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 smz_philox(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double smz_philox_uniform(unsigned long long seed, unsigned long long tree,
+                                                     unsigned index, unsigned stream) {
+  uint4 r = smz_philox(make_uint4(index >> 1, stream, (unsigned)tree, (unsigned)(tree >> 32)),
+                       make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  unsigned a = (index & 1) ? r.z : r.x, b = (index & 1) ? r.w : r.y;
+  // numpy random_sample: ((a>>5)*2^26 + (b>>6)) / 2^53 — exact in double
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double smz_uniform(const SmzArena& a, int tree, int idx) {
+  if (a.rng_mode) {
+    if (idx >= a.tape_stride) { *a.error_flag = 1; return 0.5; }
+    return a.tape_u[(size_t)tree * a.tape_stride + idx];
+  }
+  return smz_philox_uniform(a.seed_state[0], a.seed_state[1] + (unsigned long long)tree, (unsigned)idx, 0u);
+}
+#endif

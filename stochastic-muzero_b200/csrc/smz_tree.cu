@@ -1,0 +1,406 @@
+// smz_tree.cu — tree kernels of the batched Stochastic-MuZero search (sm_100a).
+//
+// G threads ("lanes") of a warp cooperate on one tree, one lane per child / per path node; G is a
+// template parameter (2..32, 32 = warp per tree).  All arithmetic that decides a visit order follows
+// the reference's numpy semantics exactly: explicit round-to-nearest
+// intrinsics (no FMA contraction), float64 pUCT prior term, float32 value term, numpy's pairwise
+// float32 summation order, RandomState.choice's cdf/searchsorted algorithm.
+//
+//   k_root_expand    monte_carlo_tree_search.py:203-225  root children + Dirichlet mixing
+//   k_select         :235-267   pUCT argmax / chance sampling descent, leaf record, branch compaction
+//   k_expand_backup  :289-308   children of the leaf + min-max discounted backup
+//   k_read_roots     game.py:179-204 consumer view (child visits, priors, rewards, root value)
+#include "smz_common.cuh"
+#include "smz_kernels.h"
+
+namespace {
+
+template <int G>
+struct Group {
+  int lane, gl, gbase;
+  unsigned gmask;
+  __device__ Group() {
+    lane = threadIdx.x & 31;
+    gl = lane & (G - 1);
+    gbase = lane & ~(G - 1);
+    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  }
+  template <typename T>
+  __device__ T bcast(T v, int src) const { return __shfl_sync(gmask, v, gbase + src); }
+  __device__ unsigned ballot(bool p) const {
+    unsigned b = __ballot_sync(gmask, p);
+    return (G == 32) ? b : ((b >> gbase) & ((1u << G) - 1u));
+  }
+};
+
+// numpy float32 add.reduce over n values held one per lane: pairwise summation with an 8-way
+// unrolled block (n >= 8) or a plain loop from 0.f (n < 8) — numpy/_core/src/umath/loops_utils.h.src.
+template <int G>
+__device__ float np_sum_f32(const Group<G>& g, float a, int n) {
+  if (G < 8 || n < 8) {
+    float r = 0.f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, g.bcast(a, i));
+    return r;
+  }
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = g.bcast(a, j);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], g.bcast(a, (i + j) & (G - 1)));
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, g.bcast(a, i));
+  return res;
+}
+
+// cdf of RandomState.choice: float64 cumsum of p (sequential), divided by the last entry.
+// Every lane i < n returns cdf[i]; lanes >= n return 2.0 (never <= u).
+template <int G>
+__device__ double choice_cdf(const Group<G>& g, double p, int n) {
+  double acc = 0.0, mine = 0.0;
+  for (int i = 0; i < n; ++i) {
+    acc = __dadd_rn(acc, g.bcast(p, i));
+    if (g.gl == i) mine = acc;
+  }
+  return (g.gl < n) ? __ddiv_rn(mine, acc) : 2.0;
+}
+
+// (policy + 1e-12) / sum in float32 (mcts.py:205-206, :291-292); lanes >= n hold 0.
+template <int G>
+__device__ float normalise_policy(const Group<G>& g, float pol, int n) {
+  float p = (g.gl < n) ? __fadd_rn(pol, 1e-12f) : 0.f;
+  float s = np_sum_f32(g, p, n);
+  return (g.gl < n) ? __fdiv_rn(p, s) : 0.f;
+}
+
+// np.random.choice(n, bound, p=p, replace=False): returns the bit set of chosen indices and advances
+// the tree's uniform cursor by the number of draws numpy would have consumed.
+template <int G>
+__device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, int tree, float p32,
+                                               int n, int bound, int& cursor) {
+  unsigned found = 0;
+  int nf = 0;
+  const double pd = (double)p32;
+  for (int round = 0; nf < bound; ++round) {
+    if (round > 2 * SMZ_MAX_POLICY) {   // NaN / degenerate policy: numpy would raise; do not hang
+      *a.error_flag = 2;
+      for (int i = 0; i < n && nf < bound; ++i)
+        if (!((found >> i) & 1u)) { found |= 1u << i; ++nf; }
+      break;
+    }
+    const int m = bound - nf;
+    const double c = choice_cdf(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n);
+    for (int j = 0; j < m; ++j) {
+      const double u = smz_uniform(a, tree, cursor + j);
+      int idx = __popc(g.ballot(c <= u));
+      idx = idx < n ? idx : n - 1;
+      if (!((found >> idx) & 1u)) { found |= 1u << idx; ++nf; }
+    }
+    cursor += m;
+  }
+  return found;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__ policy, int pstride,
+                              const int* __restrict__ root_to_play, int train,
+                              const double* __restrict__ dirichlet) {
+  Group<G> g;
+  const int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (tree >= n_trees) return;
+  const size_t tb = (size_t)tree * a.M;
+  const int n = a.A;
+  int cursor = 0;
+  const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
+  const float p = normalise_policy(g, pol, n);
+  // all A actions become children (ascending); the call still consumes its draws (T5)
+  choice_without_replacement(g, a, tree, p, n, n, cursor);
+  if (g.gl < n) {
+    double prior = (double)p;
+    if (train) {
+      const double nz = dirichlet[(size_t)tree * a.A + g.gl];
+      prior = __dadd_rn((double)__fmul_rn(p, a.one_minus_frac_f32), __dmul_rn(nz, a.frac));
+    }
+    a.root_prior[(size_t)tree * a.A + g.gl] = prior;
+    a.stat[tb + 1 + g.gl] = make_int4(0, 0, 0, __float_as_int(p));
+    a.link[tb + 1 + g.gl] = make_int2(0, g.gl);
+  }
+  if (g.gl == 0) {
+    a.stat[tb] = make_int4(0, 0, 0, 0);
+    a.link[tb] = make_int2(1, -1);
+    a.minmax[tree] = make_float2(__int_as_float(0x7f800000), __int_as_float(0xff800000));
+    a.ucursor[tree] = cursor;
+    a.root_to_play[tree] = root_to_play ? root_to_play[tree] : 0;
+    a.path_len[tree] = 0;
+    if (a.rec_root_policy)
+      for (int i = 0; i < a.W; ++i) a.rec_root_policy[(size_t)tree * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_slot, int* __restrict__ o_action,
+                         int* __restrict__ o_branch) {
+  Group<G> g;
+  const int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (tree >= n_trees) return;
+  const size_t tb = (size_t)tree * a.M;
+  int cursor = a.ucursor[tree];
+  const float2 mm = a.minmax[tree];
+  const float vmin = mm.x, vmax = mm.y;
+  int* path = a.path + (size_t)tree * a.path_stride;
+
+  int depth = 0, cbase = 1, nch = a.A;
+  int parent_visit = a.stat[tb].x;
+  if (g.gl == 0) path[0] = 0;
+  int L = 1, child = 0, child_key = 0;
+  for (;;) {
+    const bool act = g.gl < nch;
+    int4 st = make_int4(0, 0, 0, 0);
+    int2 lk = make_int2(0, 0);
+    if (act) { st = a.stat[tb + cbase + g.gl]; lk = a.link[tb + cbase + g.gl]; }
+    int pick;
+    if ((depth >> 1) & 1) {
+      // chance node: sample a child from the smoothed priors (mcts.py:249-255, T9)
+      const float p = __int_as_float(st.w);
+      const float om = act ? __fadd_rn(__fsub_rn(1.f, p), 1e-12f) : 0.f;
+      const float rem = fabsf(__fdiv_rn(np_sum_f32(g, om, nch), (float)nch));
+      const float sh = act ? __fadd_rn(p, rem) : 0.f;
+      const float q = act ? __fdiv_rn(sh, np_sum_f32(g, sh, nch)) : 0.f;
+      const double c = choice_cdf(g, (double)q, nch);
+      const double u = smz_uniform(a, tree, cursor);
+      cursor += 1;
+      pick = __popc(g.ballot(c <= u));
+      pick = pick < nch ? pick : nch - 1;
+    } else {
+      // decision node: argmax of ucb_score, one fresh uniform per child (mcts.py:235-243, T3/T5/T6)
+      double score = -__longlong_as_double(0x7ff0000000000000LL);
+      if (act) {
+        const double prior = (depth == 0) ? a.root_prior[(size_t)tree * a.A + g.gl] : (double)__int_as_float(st.w);
+        const double u = smz_uniform(a, tree, cursor + g.gl);
+        const double pb_c = a.pbc[parent_visit];
+        const double ps = __ddiv_rn(__dmul_rn(__dmul_rn(sqrt((double)parent_visit), pb_c), prior), (double)(st.x + 1));
+        double vs = 0.0;
+        if (st.x > 0) {
+          const float val = __fdiv_rn(__int_as_float(st.y), (float)st.x);
+          float v = __fadd_rn(__int_as_float(st.z), __fmul_rn(a.discount, val));
+          if (vmax > vmin) v = __fdiv_rn(__fsub_rn(v, vmin), __fsub_rn(vmax, vmin));
+          vs = (double)v;
+        }
+        const double noise = __dadd_rn(1e-7, __dmul_rn(2e-7 - 1e-7, u));
+        score = __dadd_rn(__dadd_rn(ps, vs), noise);
+      }
+      cursor += nch;
+      int best = act ? g.gl : -1;
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) {
+        const double os = __shfl_xor_sync(g.gmask, score, off);
+        const int ob = __shfl_xor_sync(g.gmask, best, off);
+        if (os > score || (os == score && ob > best)) { score = os; best = ob; }
+      }
+      pick = best < 0 ? 0 : best;
+    }
+    const int child_visit = g.bcast(st.x, pick);
+    const int child_cb = g.bcast(lk.x, pick);
+    child_key = g.bcast(lk.y, pick);
+    child = cbase + pick;
+    if (g.gl == 0) path[L] = child;
+    ++L;
+    if (child_cb == 0 || L >= a.path_stride) break;
+    // the child (depth+1) was expanded through the dynamics pair iff this node is a chance node (T2)
+    nch = ((depth >> 1) & 1) ? a.Kd : a.Kc;
+    parent_visit = child_visit;
+    cbase = child_cb;
+    ++depth;
+  }
+  if (g.gl == 0) {
+    const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
+    const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
+    a.leaf_node[tree] = child;
+    a.leaf_slot[tree] = slot;
+    a.leaf_action[tree] = child_key;
+    a.leaf_branch[tree] = branch;
+    a.path_len[tree] = L;
+    a.ucursor[tree] = cursor;
+    if (o_slot) o_slot[tree] = slot;
+    if (o_action) o_action[tree] = child_key;
+    if (o_branch) o_branch[tree] = branch;
+    const int r = atomicAdd(&a.branch_count[sim * 2 + branch], 1);
+    a.rows[(size_t)branch * a.B + r] = tree;
+    atomicAdd(a.depth_sum, (unsigned long long)(depth + 1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* __restrict__ policy, int pstride,
+                                const float* __restrict__ value, const float* __restrict__ reward) {
+  Group<G> g;
+  const int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (tree >= n_trees) return;
+  const size_t tb = (size_t)tree * a.M;
+  const int leaf = a.leaf_node[tree];
+  const int branch = a.leaf_branch[tree];
+  const int L = a.path_len[tree];
+  int cursor = a.ucursor[tree];
+  const int* path = a.path + (size_t)tree * a.path_stride;
+
+  // children of the leaf (mcts.py:289-297): width C after the afterstate pair, A after dynamics
+  const int n = branch ? a.A : a.C;
+  const int bound = min(a.K, n);
+  const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
+  const float p = normalise_policy(g, pol, n);
+  const unsigned found = choice_without_replacement(g, a, tree, p, n, bound, cursor);
+  const int cb = 1 + a.A + sim * a.Kmax;
+  if (g.gl < n && ((found >> g.gl) & 1u)) {
+    const int r = __popc(found & ((1u << g.gl) - 1u));
+    a.stat[tb + cb + r] = make_int4(0, 0, 0, __float_as_int(p));
+    a.link[tb + cb + r] = make_int2(0, g.gl);
+  }
+  float v = value[tree];
+  const float rew = branch ? reward[tree] : 0.f;
+  if (g.gl == 0) {
+    a.link[tb + leaf].x = cb;
+    a.ucursor[tree] = cursor;
+    if (a.rec_policy) {
+      const size_t ro = ((size_t)tree * a.N + sim);
+      for (int i = 0; i < a.W; ++i) a.rec_policy[ro * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
+      a.rec_value[ro] = v;
+      a.rec_reward[ro] = rew;
+      a.rec_branch[ro] = (signed char)branch;
+    }
+  }
+
+  // backup leaf -> root (mcts.py:299-308): lanes own path levels, the discounted return is a serial
+  // float32 recurrence (mul then add, two roundings) carried through shuffles
+  const signed char* sign = a.sign + (size_t)a.root_to_play[tree] * (a.N + 2);
+  float2 mm = a.minmax[tree];
+  const int n_chunks = (L + G - 1) / G;
+  for (int chunk = n_chunks - 1; chunk >= 0; --chunk) {
+    const int l = chunk * G + g.gl;
+    const bool valid = l < L;
+    int node = 0;
+    int4 st = make_int4(0, 0, 0, 0);
+    if (valid) {
+      node = path[l];
+      st = a.stat[tb + node];
+      if (l == L - 1 && branch) st.z = __float_as_int(rew);
+    }
+    const float r = __int_as_float(st.z);
+    float myv = 0.f;
+    const int hi = min(L, (chunk + 1) * G) - 1;
+    for (int i = hi; i >= chunk * G; --i) {
+      if (l == i) myv = v;
+      const float ri = g.bcast(r, i - chunk * G);
+      v = __fadd_rn(ri, __fmul_rn(a.discount, v));
+    }
+    if (valid) {
+      const float vs = __fadd_rn(__int_as_float(st.y), sign[l] > 0 ? myv : -myv);
+      st.x += 1;
+      st.y = __float_as_int(vs);
+      a.stat[tb + node] = st;
+      const float nv = __fdiv_rn(vs, (float)st.x);
+      mm.x = fminf(mm.x, nv);
+      mm.y = fmaxf(mm.y, nv);
+    }
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) {
+    mm.x = fminf(mm.x, __shfl_xor_sync(g.gmask, mm.x, off));
+    mm.y = fmaxf(mm.y, __shfl_xor_sync(g.gmask, mm.y, off));
+  }
+  if (g.gl == 0) a.minmax[tree] = mm;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_read_roots(SmzArena a, int n_trees, int* __restrict__ visits, float* __restrict__ values,
+                             double* __restrict__ priors, float* __restrict__ rewards) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_trees * a.A) return;
+  const int tree = i / a.A, c = i % a.A;
+  const size_t tb = (size_t)tree * a.M;
+  const int4 st = a.stat[tb + 1 + c];
+  if (visits) visits[i] = st.x;
+  if (rewards) rewards[i] = __int_as_float(st.z);
+  if (priors) priors[i] = a.root_prior[i];
+  if (values && c == 0) {
+    const int4 r = a.stat[tb];
+    values[tree] = r.x == 0 ? 0.f : __fdiv_rn(__int_as_float(r.y), (float)r.x);
+  }
+}
+
+// Dirichlet(alpha) per tree on the device: Gamma(alpha) by Marsaglia-Tsang (alpha+1 boost), Philox
+// stream 1.  Production mode only; parity runs pass recorded noise (np.random.dirichlet, mcts.py:220).
+__global__ void k_dirichlet(SmzArena a, int n_trees) {
+  const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= n_trees) return;
+  unsigned ctr = 0;
+  const unsigned long long seed = a.seed_state[0], tid = a.seed_state[1] + (unsigned long long)tree;
+  auto U = [&]() { double u = smz_philox_uniform(seed, tid, ctr++, 1u); return u > 0.0 ? u : 1.0 / 9007199254740992.0; };
+  double sum = 0.0;
+  for (int i = 0; i < a.A; ++i) {
+    const double al = a.alpha;
+    const double d = (al < 1.0 ? al + 1.0 : al) - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double gsample = d;
+    for (int it = 0; it < 256; ++it) {
+      const double u1 = U(), u2 = U();
+      const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+      const double t = 1.0 + c * x;
+      if (t <= 0.0) continue;
+      const double v3 = t * t * t, u = U();
+      if (log(u) < 0.5 * x * x + d - d * v3 + d * log(v3)) { gsample = d * v3; break; }
+    }
+    if (al < 1.0) gsample *= pow(U(), 1.0 / al);
+    a.dirichlet[(size_t)tree * a.A + i] = gsample;
+    sum += gsample;
+  }
+  for (int i = 0; i < a.A; ++i) a.dirichlet[(size_t)tree * a.A + i] /= (sum > 0.0 ? sum : 1.0);
+}
+
+template <int G>
+int grid_for(int n_trees, int threads) { return (int)(((long long)n_trees * G + threads - 1) / threads); }
+
+}  // namespace
+
+#define SMZ_DISPATCH_G(G_, CALL)        \
+  switch (G_) {                         \
+    case 2: { constexpr int G = 2; CALL; } break;   \
+    case 4: { constexpr int G = 4; CALL; } break;   \
+    case 8: { constexpr int G = 8; CALL; } break;   \
+    case 16: { constexpr int G = 16; CALL; } break; \
+    default: { constexpr int G = 32; CALL; } break; \
+  }
+
+static const int kThreads = 128;
+
+void smz_launch_root_expand(const SmzArena& a, int lanes, int n_trees, const float* policy, int pstride,
+                            const int* root_to_play, int train, const double* dirichlet, cudaStream_t s) {
+  SMZ_DISPATCH_G(lanes, (k_root_expand<G><<<grid_for<G>(n_trees, kThreads), kThreads, 0, s>>>(
+                            a, n_trees, policy, pstride, root_to_play, train, dirichlet)));
+}
+
+void smz_launch_select(const SmzArena& a, int lanes, int n_trees, int sim, int* o_slot, int* o_action, int* o_branch,
+                       cudaStream_t s) {
+  SMZ_DISPATCH_G(lanes, (k_select<G><<<grid_for<G>(n_trees, kThreads), kThreads, 0, s>>>(a, n_trees, sim, o_slot,
+                                                                                         o_action, o_branch)));
+}
+
+void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim, const float* policy, int pstride,
+                              const float* value, const float* reward, cudaStream_t s) {
+  SMZ_DISPATCH_G(lanes, (k_expand_backup<G><<<grid_for<G>(n_trees, kThreads), kThreads, 0, s>>>(
+                            a, n_trees, sim, policy, pstride, value, reward)));
+}
+
+void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,
+                           cudaStream_t s) {
+  const int n = n_trees * a.A;
+  k_read_roots<<<(n + 255) / 256, 256, 0, s>>>(a, n_trees, visits, values, priors, rewards);
+}
+
+void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s) {
+  k_dirichlet<<<(n_trees + 127) / 128, 128, 0, s>>>(a, n_trees);
+}

@@ -1,0 +1,349 @@
+"""Drop-in replacement for the reference's ``monte_carlo_tree_search.py`` backed by the CUDA engine.
+
+Same call surface as /root/reference/monte_carlo_tree_search.py — ``Node`` (:6-21), ``MinMaxStats``
+(:24-36), ``Player_cycle`` (:38-72), ``Monte_carlo_tree_search.__init__/reset/run`` (:75-349) — as
+consumed by self_play.py:46/:85/:419 and muzero_cli.py:131-139, plus the additive batched entry
+``run_batch`` (thousands of independent trees per call).  The tree lives in the engine's HBM arena;
+``run`` returns a ``Node`` view materialised from it, so ``root.children[a].visit_count``,
+``.prior``, ``.reward`` and ``root.value()`` (all that game.py:179-235 touches) behave as before.
+
+Two ways a model can be attached:
+  * a reference-style ``Muzero`` with ``model_structure == "mlp_model"``: its six modules are packed
+    once (weights.pack_weights) and the whole search, network step included, runs on the GPU;
+  * any other object exposing the five ``*_function_inference`` methods (other model families, test
+    stubs): the tree kernels run on the GPU and the model is called back on the host once per
+    simulation, like the reference does (:271-286).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .engine import SearchEngine, _is_chance
+from .weights import pack_weights, shape_of, weights_version
+
+
+class Node(object):
+    """Per-node record, attribute-compatible with the reference's Node (:6-21)."""
+
+    __slots__ = ("visit_count", "prior", "value_sum", "children", "reward", "to_play", "is_chance",
+                 "_hidden", "_hidden_fetch")
+
+    def __init__(self, prior: float):
+        self.visit_count = 0
+        self.prior = prior
+        self.value_sum = 0
+        self.children = {}
+        self.reward = 0
+        self.to_play = -1
+        self.is_chance = False
+        self._hidden = 0
+        self._hidden_fetch = None
+
+    @property
+    def hidden_state(self):
+        if self._hidden_fetch is not None:
+            self._hidden, self._hidden_fetch = self._hidden_fetch(), None
+        return self._hidden
+
+    @hidden_state.setter
+    def hidden_state(self, value):
+        self._hidden, self._hidden_fetch = value, None
+
+    def expanded(self):
+        return len(self.children) > 0
+
+    def value(self) -> float:
+        if self.visit_count == 0:
+            return 0
+        return self.value_sum / self.visit_count
+
+
+class MinMaxStats(object):
+    """Running bounds of the node values seen during one search (:24-36)."""
+
+    def __init__(self, minimum=float("inf"), maximum=-float("inf")):
+        self.maximum = maximum
+        self.minimum = minimum
+
+    def update(self, value: float):
+        self.maximum = max(self.maximum, value)
+        self.minimum = min(self.minimum, value)
+
+    def normalize(self, value: float) -> float:
+        if self.maximum > self.minimum:
+            return (value - self.minimum) / (self.maximum - self.minimum)
+        return value
+
+
+class Player_cycle:
+    """to_play bookkeeping (:38-72): modular cycle over ``number_of_player`` or a custom "1>2>3" loop."""
+
+    def __init__(self, number_of_player: int = None, custom_loop: str = None):
+        self.number_of_player = number_of_player
+        self.custom_loop = custom_loop
+        if isinstance(custom_loop, str):
+            self.cycle_map = torch.tensor([float(i) for i in custom_loop.split(">")])
+        elif number_of_player is not None and number_of_player >= 1:
+            self.cycle_map = torch.arange(0, number_of_player)
+        else:
+            raise Exception("You have to provide a number of player >= 1 or a custom loop like : \"1>2>3\" ")
+        self.loop_cycle = None
+        self.global_origin = self.cycle_map[0]
+        self.global_count = 0
+
+    def _len(self):
+        return self.cycle_map.size()[0]
+
+    def proximate_player_step(self, player_index):
+        return (player_index + 1) % self._len()
+
+    def global_step(self):
+        player_in_play = self.global_count % self._len()
+        self.global_count = (1 + self.global_count) % self._len()
+        return player_in_play
+
+    def global_reset(self):
+        self.global_count = 0
+
+    def player_in_play(self, player_index):
+        return self.cycle_map[player_index % self._len()]
+
+
+def _node_tree(dump, hidden_fetch=None):
+    """Materialise Node objects from a canonical depth-first dump (engine.export_tree)."""
+    nodes, stack = [], []
+    A_root = None
+    for i in range(len(dump["depth"])):
+        d = int(dump["depth"][i])
+        prior = dump["prior"][i]
+        if d == 0:
+            node = Node(0)
+        else:
+            # root children carry float64 priors (Dirichlet mixing, :224), everything below float32
+            node = Node(np.float64(prior) if d == 1 else np.float32(prior))
+        node.visit_count = int(dump["visit"][i])
+        node.value_sum = np.float32(dump["value_sum"][i]) if node.visit_count else 0
+        node.reward = np.float32(dump["reward"][i]) if d >= 1 and _is_chance(d - 1) and dump["expanded"][i] else 0
+        node.to_play = int(dump["to_play"][i])
+        node.is_chance = bool(dump["is_chance"][i])
+        if dump["expanded"][i] and hidden_fetch is not None:
+            node._hidden_fetch = (lambda n=int(dump["node"][i]): hidden_fetch(n))
+        while stack and stack[-1][0] >= d:
+            stack.pop()
+        if stack:
+            stack[-1][1].children[np.int64(dump["key"][i])] = node
+        stack.append((d, node))
+        nodes.append(node)
+    return nodes[0]
+
+
+class BatchedRoots:
+    """Result of ``run_batch``: root statistics of B trees as device tensors + lazy ``Node`` views."""
+
+    def __init__(self, engine: SearchEngine, stats):
+        self._engine = engine
+        self.visit_counts = stats["visits"]       # int32 [B, A]
+        self.priors = stats["priors"]             # float64 [B, A]
+        self.rewards = stats["rewards"]           # float32 [B, A]
+        self.root_values = stats["root_values"]   # float32 [B]
+
+    def __len__(self):
+        return int(self.visit_counts.shape[0])
+
+    def __getitem__(self, i) -> Node:
+        return _node_tree(self._engine.export_tree(int(i)), self._hidden_fetcher(int(i)))
+
+    @property
+    def roots(self):
+        return self
+
+    def _hidden_fetcher(self, tree):
+        eng = self._engine
+        if eng.net == "external":
+            return None
+        A, kmax = eng.A, eng.dims.max_children
+
+        def fetch(node_index, _ar={}):
+            if "cb" not in _ar:
+                _ar["cb"] = eng.export_arena(tree)["child_base"]
+            cb = int(_ar["cb"][node_index])
+            slot = 0 if cb == 1 else (cb - 1 - A) // kmax + 1
+            return eng.read_hidden(slot)[tree:tree + 1].cpu()
+        return fetch
+
+
+class Monte_carlo_tree_search():
+    def __init__(self,
+                 pb_c_base=19652,
+                 pb_c_init=1.25,
+                 discount=0.95,
+                 root_dirichlet_alpha=0.25,
+                 root_exploration_fraction=0.25,
+                 num_simulations=10,
+                 maxium_action_sample=2,
+                 number_of_player=1,
+                 custom_loop=None,
+                 *, net="fp32", device=None, seed=None, max_batch=None):
+        """Same nine arguments as the reference (:76-85).  Keyword-only extras: ``net`` ("fp32" exact
+        mode or "bf16" tensor-core mode for the fused MLP step), ``device`` (CUDA ordinal), ``seed``
+        (Philox key; default drawn from numpy's global RNG so ``np.random.seed`` reproduces runs),
+        ``max_batch`` (arena capacity reserved for ``run_batch``)."""
+        self._net, self._device, self._seed, self._max_batch = net, device, seed, max_batch
+        self._engines = {}
+        self._weights_seen = {}
+        self._run_counter = 0
+        self.reset(pb_c_base, pb_c_init, discount, root_dirichlet_alpha, root_exploration_fraction,
+                   num_simulations, maxium_action_sample, number_of_player, custom_loop)
+
+    def reset(self, pb_c_base=19652, pb_c_init=1.25, discount=0.95, root_dirichlet_alpha=0.25,
+              root_exploration_fraction=0.25, num_simulations=10, maxium_action_sample=2, number_of_player=1,
+              custom_loop=None):
+        # argument checks and messages of the reference (:148-173)
+        assert isinstance(pb_c_base, int) and pb_c_base >= 1, "pb_c_base ∈ int | {1 < pb_c_base < +inf)"
+        assert isinstance(pb_c_init, float) and pb_c_init >= 0, "pb_c_init ∈ float | {0 < pb_c_init < +inf)"
+        assert isinstance(discount, (int, float)) and discount >= 0, "discount ∈ float | {0 < discount < +inf)"
+        assert isinstance(root_dirichlet_alpha, float) and 0 <= root_dirichlet_alpha <= 1, \
+            "root_dirichlet_alpha ∈ float | {0< root_dirichlet_alpha < 1)"
+        assert isinstance(root_exploration_fraction, float) and 0 <= root_exploration_fraction <= 1, \
+            "root_exploration_fraction ∈ float | {0 < root_exploration_fraction < 1)"
+        assert isinstance(maxium_action_sample, int) and maxium_action_sample >= 1, \
+            "maxium_action_sample ∈ int | {1 < maxium_action_sample < +inf)"
+        assert isinstance(num_simulations, int) and num_simulations >= 0, \
+            "num_simulations ∈ int | {0 < num_simulations < +inf)"
+        assert isinstance(number_of_player, int) and number_of_player >= 1, \
+            "number_of_player ∈ int | {1 < number_of_player < +inf)"
+        assert isinstance(custom_loop, str) or custom_loop is None, "custom_loop ∈ str | 1>2>3>3 "
+        self.pb_c_base, self.pb_c_init, self.discount = pb_c_base, pb_c_init, discount
+        self.root_dirichlet_alpha, self.root_exploration_fraction = root_dirichlet_alpha, root_exploration_fraction
+        self.maxium_action_sample, self.num_simulations = maxium_action_sample, num_simulations
+        self.number_of_player, self.custom_loop = number_of_player, custom_loop
+        self.node = None
+        self.model = None
+        self.root = None
+        self.min_max_stats = MinMaxStats()
+        self.cycle = Player_cycle(number_of_player=number_of_player, custom_loop=custom_loop)
+        for eng in self._engines.values():
+            eng.close()
+        self._engines = {}
+
+    # ------------------------------------------------------------------------------------------
+    def search_config(self):
+        return dict(pb_c_base=self.pb_c_base, pb_c_init=self.pb_c_init, discount=self.discount,
+                    root_dirichlet_alpha=self.root_dirichlet_alpha,
+                    root_exploration_fraction=self.root_exploration_fraction,
+                    num_simulations=self.num_simulations, maxium_action_sample=self.maxium_action_sample,
+                    number_of_player=self.number_of_player, custom_loop=self.custom_loop)
+
+    @classmethod
+    def from_config(cls, config: dict, **extras):
+        """Build from the JSON section "monte_carlo_tree_search" (self_play.py:639-647), verbatim."""
+        section = config.get("monte_carlo_tree_search", config)
+        keys = ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha", "root_exploration_fraction",
+                "num_simulations", "maxium_action_sample", "number_of_player", "custom_loop")
+        return cls(**{k: section[k] for k in keys if k in section}, **extras)
+
+    def _base_seed(self):
+        if self._seed is None:
+            self._seed = int(np.random.randint(0, 2 ** 31 - 1))
+        return self._seed
+
+    def _engine(self, kind, batch, action_dim, chance_dim, shape=None):
+        cap = max(batch, self._max_batch or 1)
+        key = (kind, action_dim, chance_dim, shape)
+        eng = self._engines.get(key)
+        if eng is None or eng.max_trees < batch:
+            if eng is not None:
+                eng.close()
+            eng = SearchEngine(self.search_config(), action_dim, chance_dim, max_trees=cap, model_shape=shape,
+                               net=kind, rng="philox", seed=self._base_seed(), device=self._device)
+            self._engines[key] = eng
+            self._weights_seen.pop(key, None)
+        return eng, key
+
+    @staticmethod
+    def _is_fusable(model):
+        return getattr(model, "model_structure", None) == "mlp_model" and all(
+            hasattr(model, f"{n}_function") for n in ("representation", "prediction", "afterstate_prediction",
+                                                      "afterstate_dynamics", "dynamics", "encoder"))
+
+    def _next_seed(self):
+        self._run_counter += 1
+        return (self._base_seed() + 0x9E3779B97F4A7C15 * self._run_counter) & 0xFFFFFFFFFFFFFFFF
+
+    # ------------------------------------------------------------------------------------------
+    def run_batch(self, observations, model=None, train=True, root_to_play=None) -> BatchedRoots:
+        """B independent searches in one call.  ``observations``: float tensor/array [B, obs_dim]
+        (host or device).  Returns BatchedRoots (device tensors; ``roots[i]`` gives a Node view)."""
+        if not self._is_fusable(model):
+            raise TypeError("run_batch needs a reference-style MLP Muzero (model_structure == 'mlp_model'); "
+                            "other models go through run(), one tree at a time")
+        self.model = model
+        shape = shape_of(model)
+        obs = observations if torch.is_tensor(observations) else torch.as_tensor(np.asarray(observations))
+        obs = obs.reshape(obs.shape[0], -1)
+        eng, key = self._engine(self._net, obs.shape[0], shape.action_dim, shape.chance_dim, shape)
+        ver = weights_version(model)
+        if self._weights_seen.get(key) != ver:
+            blob, _ = pack_weights(model)
+            eng.set_weights(blob)
+            self._weights_seen[key] = ver
+        eng.set_seed(self._next_seed())
+        eng.root(obs=obs, root_to_play=root_to_play, train=train)
+        eng.simulate(self.num_simulations)
+        return BatchedRoots(eng, eng.read_roots())
+
+    def run(self, observation=None, model=None, train=True):
+        """One search, reference signature (:311).  Returns the root Node."""
+        self.model = model
+        to_play = self.cycle.global_step()
+        if self._is_fusable(model):
+            obs = observation if torch.is_tensor(observation) else torch.as_tensor(np.asarray(observation))
+            batch = self.run_batch(obs.reshape(1, -1), model, train,
+                                   root_to_play=torch.tensor([to_play], dtype=torch.int32))
+            eng = batch._engine
+            dump = eng.export_tree(0)
+            self.root = _node_tree(dump, batch._hidden_fetcher(0))
+        else:
+            self.root = self._run_callback(observation, model, train, to_play)
+            return self.root
+        self.min_max_stats = MinMaxStats(np.float32(dump["minmax"][0]), np.float32(dump["minmax"][1]))
+        self.node = self.root
+        return self.root
+
+    def _run_callback(self, observation, model, train, to_play):
+        """Host-model mode: tree kernels on the GPU, the five inference methods called back per
+        simulation (:182, :198, :271-286)."""
+        h0 = model.representation_function_inference(observation)
+        policy, _value = model.prediction_function_inference(h0)
+        policy = np.asarray(policy, dtype=np.float32).reshape(1, -1)
+        A = policy.shape[1]
+        eng, _ = self._engine("external", 1, A, getattr(model, "chance_dimension", A))
+        eng.set_seed(self._next_seed())
+        eng.root(root_policy=policy, root_to_play=torch.tensor([to_play], dtype=torch.int32), train=train)
+        hidden = {0: h0}
+        for sim in range(self.num_simulations):
+            slot, action, branch = (int(t.item()) for t in eng.select(sim))
+            if branch:
+                reward, h = model.dynamics_function_inference(hidden[slot], np.int64(action))
+                policy, value = model.prediction_function_inference(h)
+            else:
+                reward = 0.0
+                h = model.afterstate_dynamics_function_inference(hidden[slot], np.int64(action))
+                policy, value = model.afterstate_prediction_function_inference(h)
+            hidden[sim + 1] = h
+            eng.expand_backup(sim, np.asarray(policy, dtype=np.float32).reshape(1, -1),
+                              np.array([value], dtype=np.float32), np.array([reward], dtype=np.float32))
+        dump = eng.export_tree(0)
+        kmax = eng.dims.max_children
+        arena_cb = eng.export_arena(0)["child_base"]
+
+        def fetch(node_index):
+            cb = int(arena_cb[node_index])
+            return hidden[0 if cb == 1 else (cb - 1 - A) // kmax + 1]
+        root = _node_tree(dump, fetch)
+        self.min_max_stats = MinMaxStats(np.float32(dump["minmax"][0]), np.float32(dump["minmax"][1]))
+        self.node = root
+        return root

@@ -1,0 +1,263 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA engine, called through the C ABI,
+against the committed outputs of the reference (tests/golden) and against the CPU oracle.
+
+Bars (BASELINE.json north_star): with identical recorded network outputs and RNG draws, visit counts,
+selected actions, sampled chance codes — and in fact every node statistic — are BIT-EXACT; the fp32
+network step agrees with the reference's torch fp32 within 1e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_io
+from oracle import mcts_oracle as O
+from oracle import net_oracle as NO
+
+pytestmark = pytest.mark.gpu
+
+NET_ATOL = 1e-5          # fp32 CUDA-core network step vs reference torch fp32 (north_star tolerance)
+
+
+def _engine_for(z, **kw):
+    from stochastic_muzero_b200 import SearchEngine
+    c = z["config"]
+    return SearchEngine(c, action_dim=c["action_dim"], chance_dim=c["chance_dim"], **kw)
+
+
+def _replay_tape(z, lanes=0):
+    """Drive the tree kernels with the recorded draws and recorded network outputs."""
+    c = z["config"]
+    B, N = len(z["n_nodes"]), c["num_simulations"]
+    eng = _engine_for(z, max_trees=B, net="external", rng="tape", lanes_per_tree=lanes)
+    eng.set_uniform_tape(torch.from_numpy(z["uniforms"]))
+    eng.root(root_policy=torch.from_numpy(z["root_policy"]), root_to_play=torch.from_numpy(z["exp_root_to_play"]),
+             train=z["train"], dirichlet=torch.from_numpy(z["dirichlet"]))
+    actions, branches = [], []
+    pol, val, rew = (torch.from_numpy(z[k]).cuda() for k in ("sim_policy", "sim_value", "sim_reward"))
+    for s in range(N):
+        _slot, action, branch = eng.select(s)
+        actions.append(action.cpu().numpy())
+        branches.append(branch.cpu().numpy())
+        eng.expand_backup(s, pol[:, s].contiguous(), val[:, s].contiguous(), rew[:, s].contiguous())
+    eng.stats()   # raises if the tape ran dry or a policy was degenerate
+    return eng, np.array(actions).T.reshape(B, N), np.array(branches).T.reshape(B, N)
+
+
+@pytest.mark.parametrize("name", golden_io.tree_cases())
+def test_tree_kernels_replay_reference_tapes_bit_exact(name):
+    z = golden_io.load_tree_case(name)
+    eng, actions, branches = _replay_tape(z)
+    B = len(z["n_nodes"])
+    if z["config"]["num_simulations"]:
+        assert np.array_equal(actions, z["sim_action"]), "selected leaf actions / sampled chance codes differ"
+        assert np.array_equal(branches, z["sim_branch"].astype(np.int32)), "afterstate/dynamics branch differs"
+    for b in range(B):
+        got = eng.export_tree(b)
+        assert got["n_uniforms"] == z["n_uniforms"][b], "engine consumed a different number of uniform draws"
+        golden_io.assert_dump_equal(got, golden_io.expected_dump(z, b), f"{name}[{b}]")
+    # read-out used by game.py:179-204
+    out = eng.read_roots()
+    A = z["config"]["action_dim"]
+    for b in range(B):
+        e = golden_io.expected_dump(z, b)
+        kids = np.flatnonzero(e["depth"] == 1)
+        assert np.array_equal(out["visits"][b].cpu().numpy(), e["visit"][kids])
+        assert np.array_equal(out["priors"][b].cpu().numpy(), e["prior"][kids])
+        rv = np.float32(0) if e["visit"][0] == 0 else np.float32(e["value_sum"][0] / np.float32(e["visit"][0]))
+        assert out["root_values"][b].item() == rv
+    eng.close()
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
+def test_lanes_per_tree_do_not_change_results(lanes):
+    z = golden_io.load_tree_case("a2c2k2_n50_train")
+    eng, actions, _ = _replay_tape(z, lanes=lanes)
+    assert np.array_equal(actions, z["sim_action"])
+    for b in range(len(z["n_nodes"])):
+        golden_io.assert_dump_equal(eng.export_tree(b), golden_io.expected_dump(z, b), f"lanes={lanes}[{b}]")
+    eng.close()
+
+
+def test_wide_policy_with_32_lanes_only():
+    z = golden_io.load_tree_case("a4c32k4_n50")
+    with pytest.raises(ValueError):
+        _engine_for(z, max_trees=2, net="external", rng="tape", lanes_per_tree=8)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _net_engine(z, B=64, **kw):
+    from stochastic_muzero_b200 import ModelShape, SearchEngine
+    obs, A, C, S, H, L = [int(v) for v in z["dims"]]
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=kw.pop("N", 50),
+                  maxium_action_sample=kw.pop("K", 2), number_of_player=1, custom_loop=None)
+    eng = SearchEngine(search, A, C, max_trees=B, model_shape=ModelShape(obs, A, C, S, H, L),
+                       net=kw.pop("net", "fp32"), **kw)
+    eng.set_weights(z["weights"])
+    return eng
+
+
+@pytest.mark.parametrize("name", golden_io.net_cases())
+def test_fp32_network_step_matches_reference_inference(name):
+    z = golden_io.load_net_case(name)
+    eng = _net_engine(z)
+    tol = dict(atol=NET_ATOL, rtol=1e-5)
+    np.testing.assert_allclose(eng.net_eval("repr", z["obs"])["hidden"].cpu().numpy(), z["repr_h"], **tol)
+    o = eng.net_eval("pred", z["repr_h"])
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["pred_policy"], **tol)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["pred_value"], **tol)
+    np.testing.assert_allclose(eng.net_eval("adyn", z["repr_h"], z["actions"])["hidden"].cpu().numpy(), z["adyn_h"], **tol)
+    o = eng.net_eval("apred", z["adyn_h"])
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["apred_policy"], **tol)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["apred_value"], **tol)
+    o = eng.net_eval("dyn", z["adyn_h"], z["actions"])
+    np.testing.assert_allclose(o["hidden"].cpu().numpy(), z["dyn_h"], **tol)
+    np.testing.assert_allclose(o["reward"].cpu().numpy(), z["dyn_reward"], **tol)
+    o = eng.net_eval("enc", z["obs"])
+    np.testing.assert_allclose(o["probs"].cpu().numpy(), z["enc_probs"], **tol)
+    close = np.abs(z["enc_probs"].max(1) - np.sort(z["enc_probs"], 1)[:, -2]) < 1e-5
+    assert np.array_equal(o["code"].cpu().numpy()[~close], z["enc_code"][~close])
+    eng.close()
+
+
+def _oracle_cfg(c):
+    return O.SearchConfig(**{k: c[k] for k in ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha",
+                                                "root_exploration_fraction", "num_simulations",
+                                                "maxium_action_sample", "number_of_player", "custom_loop")})
+
+
+@pytest.mark.parametrize("name", ["mlp450_seed0", "ckpt450", "mlp_small", "mlp_l0"])
+def test_full_search_with_internal_network_vs_reference(name):
+    """Real-MLP recorded searches: obs + recorded draws in, engine runs its own fp32 network.
+    (1) every network output the engine produced matches what the reference produced at the same
+    simulation within 1e-5 as long as the paths coincide, (2) replaying the engine's OWN recorded
+    outputs through the CPU oracle reproduces the engine's tree bit-exactly, (3) root values / visit
+    policies agree with the reference within 1e-5 / exactly unless a sub-1e-5 score tie flipped."""
+    z = golden_io.load_tree_case(name)
+    zn = golden_io.load_net_case(name)
+    c = z["config"]
+    B, N = len(z["n_nodes"]), c["num_simulations"]
+    eng = _net_engine(zn, B=B, N=N, K=c["maxium_action_sample"], rng="tape", record=True)
+    eng.set_uniform_tape(torch.from_numpy(z["uniforms"]))
+    eng.root(obs=torch.from_numpy(z["obs"]), train=True, dirichlet=torch.from_numpy(z["dirichlet"]))
+    eng.simulate(N)
+    eng.stats()
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    S = int(zn["dims"][3])
+    np.testing.assert_allclose(eng.read_hidden(0).cpu().numpy(), z["root_hidden"], atol=NET_ATOL, rtol=1e-5)
+    np.testing.assert_allclose(rec["root_policy"][:, :c["action_dim"]], z["root_policy"], atol=NET_ATOL, rtol=1e-5)
+    identical = 0
+    for b in range(B):
+        got = eng.export_tree(b)
+        # (2) oracle replay of the engine's own record
+        rng = O.TapeUniforms(z["uniforms"][b])
+        model = O.TapeModel(rec["root_policy"][b, :c["action_dim"]], rec["sim_policy"][b],
+                            np.where(rec["sim_branch"][b] == 1, c["action_dim"], c["chance_dim"]),
+                            rec["sim_value"][b], rec["sim_reward"][b])
+        tree = O.search(_oracle_cfg(c), model, rng, train=True, dirichlet=z["dirichlet"][b])
+        golden_io.assert_dump_equal(got, tree.dump(), f"{name}[{b}] engine vs oracle on engine record")
+        assert rng.cursor == got["n_uniforms"]
+        # (1) network outputs along the common prefix of simulations
+        same = 0
+        while same < N and rec["sim_branch"][b, same] == z["sim_branch"][b, same] and \
+                tree.paths[same] == list(z["exp_paths"][b, same][z["exp_paths"][b, same] >= 0]):
+            same += 1
+        w = z["sim_policy"].shape[2]
+        np.testing.assert_allclose(rec["sim_policy"][b, :same, :w], z["sim_policy"][b, :same], atol=NET_ATOL, rtol=1e-5)
+        np.testing.assert_allclose(rec["sim_value"][b, :same], z["sim_value"][b, :same], atol=NET_ATOL, rtol=1e-5)
+        np.testing.assert_allclose(rec["sim_reward"][b, :same], z["sim_reward"][b, :same], atol=NET_ATOL, rtol=1e-5)
+        hid = np.stack([eng.read_hidden(s + 1)[b].cpu().numpy() for s in range(same)]) if same else np.zeros((0, S))
+        np.testing.assert_allclose(hid, z["sim_hidden"][b, :same], atol=NET_ATOL, rtol=1e-5)
+        # (3) against the reference's tree
+        e = golden_io.expected_dump(z, b)
+        if same == N:
+            identical += 1
+            assert np.array_equal(got["visit"], e["visit"]) and np.array_equal(got["key"], e["key"])
+            np.testing.assert_allclose(got["value_sum"] / np.maximum(got["visit"], 1),
+                                       e["value_sum"] / np.maximum(e["visit"], 1), atol=1e-5, rtol=1e-5)
+            np.testing.assert_allclose(got["prior"], e["prior"], atol=1e-5, rtol=1e-5)
+    assert identical >= B - 1, f"only {identical}/{B} searches followed the reference's visiting order"
+    eng.close()
+
+
+def test_philox_device_matches_oracle_and_engine_record_replays():
+    """Production mode (device Philox + device Dirichlet + fp32 network): the engine's own record,
+    replayed by the oracle with the oracle's Philox restatement, gives the same tree bit for bit."""
+    zn = golden_io.load_net_case("mlp450_seed0")
+    B, N, seed, offset = 96, 50, 1234, 7
+    eng = _net_engine(zn, B=B, N=N, rng="philox", seed=seed, tree_id_offset=offset, record=True)
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(0))
+    eng.root(obs=obs, train=True)
+    eng.simulate(N)
+    st = eng.stats()
+    assert 1.0 < st["mean_leaf_depth"] < 12.0
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    assert np.allclose(rec["dirichlet"].sum(1), 1.0) and (rec["dirichlet"] >= 0).all()
+    cfg = O.SearchConfig(discount=0.997, num_simulations=N, maxium_action_sample=2)
+    for b in range(0, B, 7):
+        model = O.TapeModel(rec["root_policy"][b, :2], rec["sim_policy"][b], np.full(N, 2), rec["sim_value"][b],
+                            rec["sim_reward"][b])
+        rng = O.PhiloxUniforms(seed, offset + b)
+        tree = O.search(cfg, model, rng, train=True, dirichlet=rec["dirichlet"][b])
+        got = eng.export_tree(b)
+        golden_io.assert_dump_equal(got, tree.dump(), f"philox[{b}]")
+        assert rng.cursor == got["n_uniforms"]
+    # same seed, second search: set_seed makes it reproducible, a new seed makes it different
+    v1 = eng.read_roots()["visits"].cpu().numpy().copy()
+    eng.set_seed(seed, offset); eng.root(obs=obs, train=True); eng.simulate(N)
+    assert np.array_equal(eng.read_roots()["visits"].cpu().numpy(), v1)
+    eng.set_seed(seed + 1, offset); eng.root(obs=obs, train=True); eng.simulate(N)
+    assert not np.array_equal(eng.read_roots()["visits"].cpu().numpy(), v1)
+    eng.close()
+
+
+def test_dirichlet_device_sampler_statistics():
+    zn = golden_io.load_net_case("mlp450_seed0")
+    B = 4096
+    eng = _net_engine(zn, B=B, N=1, rng="philox", seed=5, record=True)
+    eng.root(obs=torch.zeros(B, 4), train=True)
+    d = eng.read_record()["dirichlet"].cpu().numpy()
+    # Dirichlet(0.25, 0.25): marginal Beta(0.25, 0.25): mean 0.5, var = 0.25/(4*1.5) = 1/6
+    assert abs(d[:, 0].mean() - 0.5) < 0.03 and abs(d[:, 0].var() - 1 / 6) < 0.02
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_dropin_run_with_reference_shaped_mlp():
+    from fake_muzero import FakeMuzero
+    from stochastic_muzero_b200 import Monte_carlo_tree_search
+    zn = golden_io.load_net_case("mlp450_seed0")
+    model = FakeMuzero(zn["weights"], *[int(v) for v in zn["dims"]])
+    mcts = Monte_carlo_tree_search(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                                   root_exploration_fraction=0.25, num_simulations=50, maxium_action_sample=2,
+                                   number_of_player=1, custom_loop=None, seed=3)
+    root = mcts.run(observation=torch.randn(1, 4), model=model, train=True)
+    assert sorted(root.children.keys()) == [0, 1]
+    assert sum(c.visit_count for c in root.children.values()) == 50 and root.visit_count == 50
+    assert isinstance(root.children[0].prior, np.float64) and abs(sum(c.prior for c in root.children.values()) - 1) < 1e-6
+    assert np.isfinite(root.value()) and root.hidden_state.shape == (1, 61)
+    # batched entry: same model, many observations
+    obs = torch.randn(256, 4)
+    roots = mcts.run_batch(obs, model, train=True)
+    assert roots.visit_counts.shape == (256, 2) and (roots.visit_counts.sum(1) == 50).all()
+    one = roots[5]
+    assert [c.visit_count for c in one.children.values()] == roots.visit_counts[5].tolist()
+    h = NO.NetOracle(zn["weights"], *[int(v) for v in zn["dims"]]).representation(obs[5:6].numpy())
+    np.testing.assert_allclose(one.hidden_state.numpy(), h, atol=1e-5)
+
+
+def test_dropin_run_with_callback_model_matches_oracle_statistics():
+    """Host-model mode: the tree kernels drive an arbitrary duck-typed model (here the network oracle
+    behind the reference's five inference methods)."""
+    from fake_muzero import FakeMuzero
+    from stochastic_muzero_b200 import Monte_carlo_tree_search
+    zn = golden_io.load_net_case("mlp_small")
+    model = FakeMuzero(zn["weights"], *[int(v) for v in zn["dims"]])
+    model.model_structure = "lstm_model"      # not fusable -> callback path
+    mcts = Monte_carlo_tree_search(discount=0.997, num_simulations=20, maxium_action_sample=3, seed=11)
+    root = mcts.run(observation=np.zeros((1, 5), np.float32), model=model, train=True)
+    assert root.visit_count == 20 and sum(c.visit_count for c in root.children.values()) == 20
+    assert len(root.children) == 3 and all(not c.is_chance for c in root.children.values())
+    deep = [c for c in root.children.values() if c.expanded()][0]
+    assert all(g.is_chance for g in deep.children.values())
+    assert deep.hidden_state.shape == (1, 11)

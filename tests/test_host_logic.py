@@ -1,0 +1,131 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/smz.h declares, the
+weight hand-off layout, Player_cycle tables and the drop-in call surface."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_io
+from fake_muzero import FakeMuzero
+from oracle import mcts_oracle as O
+from oracle import net_oracle as NO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from stochastic_muzero_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "smz.h")).read()
+    declared = set(re.findall(r"\b(smz_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in include/smz.h"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libsmz.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), "ctypes SIGNATURES and include/smz.h disagree"
+
+
+def test_create_rejects_bad_config_without_gpu_work():
+    import ctypes as C
+    from stochastic_muzero_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.smz_config()
+    cfg.abi_version = 999
+    h = C.c_void_p()
+    assert lib.smz_create(C.byref(cfg), C.byref(h)) == _lib.SMZ_E_INVALID_ARG
+    assert b"abi_version" in lib.smz_last_error()
+    cfg.abi_version = _lib.SMZ_ABI_VERSION
+    cfg.max_trees, cfg.num_simulations, cfg.action_dim, cfg.chance_dim = 4, 5, 64, 2
+    cfg.max_action_sample, cfg.pb_c_base, cfg.pb_c_init, cfg.discount = 2, 19652, 1.25, 0.99
+    assert lib.smz_create(C.byref(cfg), C.byref(h)) == _lib.SMZ_E_CAPACITY
+
+
+def test_blob_layout_matches_oracle_layout():
+    from stochastic_muzero_b200.weights import ModelShape, blob_layout
+    for dims in [(4, 2, 2, 61, 126, 4), (16, 4, 32, 61, 126, 4), (5, 3, 3, 11, 14, 2), (4, 2, 2, 31, 64, 0)]:
+        mine, total = blob_layout(ModelShape(*dims))
+        theirs, total2 = NO.blob_layout(*dims)
+        assert total == total2 and mine == theirs
+
+
+@pytest.mark.parametrize("name", golden_io.net_cases())
+def test_pack_weights_roundtrip(name):
+    from stochastic_muzero_b200.weights import pack_weights, shape_of
+    z = golden_io.load_net_case(name)
+    dims = [int(v) for v in z["dims"]]
+    fake = FakeMuzero(z["weights"], *dims)
+    blob, shape = pack_weights(fake)
+    assert (shape.obs_dim, shape.action_dim, shape.chance_dim, shape.state_dim, shape.hidden_dim,
+            shape.num_hidden_layers) == tuple(dims)
+    assert np.array_equal(blob, z["weights"])
+    assert shape_of(fake) == shape
+
+
+@pytest.mark.parametrize("players,loop", [(1, None), (2, None), (3, None), (1, "1>2>1>3")])
+def test_player_tables_follow_oracle_tree(players, loop):
+    """to_play / sign per depth must equal what the oracle's explicit Player_cycle bookkeeping gives."""
+    from stochastic_muzero_b200.engine import player_tables
+    N = 24
+    sign, to_play = player_tables(players, loop, N + 2)
+    cfg = O.SearchConfig(num_simulations=N, maxium_action_sample=2, number_of_player=players, custom_loop=loop,
+                         discount=0.99)
+    cyc = cfg.cycle_map()
+    for phase in range(len(cyc)):
+        g = np.random.default_rng(phase)
+
+        class M:
+            def root(self):
+                return None, np.array([0.5, 0.5], np.float32), np.float32(0)
+
+            def afterstate(self, sim, h, a):
+                return None, np.array([0.5, 0.5], np.float32), np.float32(g.normal())
+
+            def dynamics(self, sim, h, a):
+                return None, np.array([0.5, 0.5], np.float32), np.float32(g.normal()), np.float32(g.normal())
+        tree = O.search(cfg, M(), O.MTUniforms(phase), train=False, root_to_play=phase)
+        for n in range(len(tree.visit)):
+            d = tree.depth[n]
+            assert tree.to_play[n] == to_play[phase, d]
+            assert tree.is_chance[n] == bool((d >> 1) & 1)
+            same = cyc[tree.to_play[0] % len(cyc)] == cyc[tree.to_play[n] % len(cyc)]
+            assert sign[phase, d] == (1 if same else -1)
+
+
+def test_dropin_surface_and_asserts():
+    from stochastic_muzero_b200 import MinMaxStats, Monte_carlo_tree_search, Node, Player_cycle
+    m = Monte_carlo_tree_search(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                                root_exploration_fraction=0.25, num_simulations=50, maxium_action_sample=2,
+                                number_of_player=1, custom_loop=None)
+    for k in ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha", "root_exploration_fraction",
+              "num_simulations", "maxium_action_sample", "number_of_player", "custom_loop"):
+        assert hasattr(m, k)
+    assert m.cycle.global_step() == 0
+    m.cycle.global_reset()
+    with pytest.raises(AssertionError):
+        Monte_carlo_tree_search(pb_c_base=1.5)
+    with pytest.raises(AssertionError):
+        Monte_carlo_tree_search(pb_c_init=1)
+    with pytest.raises(AssertionError):
+        Monte_carlo_tree_search(num_simulations=-1)
+    n = Node(0.5)
+    assert not n.expanded() and n.value() == 0 and n.to_play == -1 and n.is_chance is False
+    mm = MinMaxStats()
+    assert mm.normalize(3.0) == 3.0
+    mm.update(1.0); mm.update(3.0)
+    assert mm.normalize(2.0) == 0.5
+    pc = Player_cycle(number_of_player=3)
+    assert [pc.global_step() for _ in range(4)] == [0, 1, 2, 0]
+    assert pc.proximate_player_step(2) == 0
+    pc2 = Player_cycle(custom_loop="1>2>1>3")
+    assert float(pc2.player_in_play(2)) == 1.0
+    cfg = {"monte_carlo_tree_search": m.search_config()}
+    m2 = Monte_carlo_tree_search.from_config(cfg)
+    assert m2.search_config() == m.search_config()
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors from the Random123 distribution (kat_vectors)."""
+    assert O.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert O.philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert O.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)

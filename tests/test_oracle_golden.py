@@ -30,3 +30,36 @@ def test_oracle_replays_reference_tape(name):
         for s, keys in enumerate(tree.paths):
             exp = z["exp_paths"][b, s]
             assert list(exp[exp >= 0]) == keys, f"{name}[{b}] sim {s}: path differs"
+
+
+# ---------------------------------------------------------------------------------------------------
+# network oracle vs the reference's own *_inference outputs
+# ---------------------------------------------------------------------------------------------------
+NET_TOL = 2e-6   # numpy vs torch BLAS summation order; same arithmetic otherwise
+
+
+@pytest.mark.parametrize("name", golden_io.net_cases())
+def test_net_oracle_matches_reference_inference(name):
+    from oracle import net_oracle as NO
+    z = golden_io.load_net_case(name)
+    net = NO.NetOracle(z["weights"], *[int(v) for v in z["dims"]])
+    h = net.representation(z["obs"])
+    np.testing.assert_allclose(h, z["repr_h"], atol=NET_TOL, rtol=0)
+    p, v = net.prediction(z["repr_h"])
+    np.testing.assert_allclose(p, z["pred_policy"], atol=NET_TOL, rtol=0)
+    np.testing.assert_allclose(v, z["pred_value"], atol=NET_TOL, rtol=1e-5)
+    ah = net.afterstate_dynamics(z["repr_h"], z["actions"])
+    np.testing.assert_allclose(ah, z["adyn_h"], atol=NET_TOL, rtol=0)
+    ap, av = net.afterstate_prediction(z["adyn_h"])
+    np.testing.assert_allclose(ap, z["apred_policy"], atol=NET_TOL, rtol=0)
+    np.testing.assert_allclose(av, z["apred_value"], atol=NET_TOL, rtol=1e-5)
+    r, dh = net.dynamics(z["adyn_h"], z["actions"])
+    np.testing.assert_allclose(dh, z["dyn_h"], atol=NET_TOL, rtol=0)
+    np.testing.assert_allclose(r, z["dyn_reward"], atol=NET_TOL, rtol=1e-5)
+    dp, dv = net.prediction(z["dyn_h"])
+    np.testing.assert_allclose(dp, z["dpred_policy"], atol=NET_TOL, rtol=0)
+    np.testing.assert_allclose(dv, z["dpred_value"], atol=NET_TOL, rtol=1e-5)
+    probs, code = net.encoder(z["obs"])
+    np.testing.assert_allclose(probs, z["enc_probs"], atol=NET_TOL, rtol=0)
+    margin = np.abs(z["enc_probs"][:, :1] - z["enc_probs"]).max(axis=1) if z["enc_probs"].shape[1] == 2 else None
+    assert np.array_equal(code, z["enc_code"]) or margin is not None and (margin[code != z["enc_code"]] < 1e-5).all()
