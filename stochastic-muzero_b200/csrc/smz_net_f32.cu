@@ -159,9 +159,11 @@ __device__ float support_scalar(const float* logits, int S) {
   const float z = warp_sum(e0 + e1);
   const int half = S / 2;
   const float y = warp_sum((float)(lane - half) * (e0 / z) + (float)(lane + 32 - half) * (e1 / z));
-  const float eps = 0.001f;
-  const float t = (sqrtf(1.f + 4.f * eps * (fabsf(y) + 1.f + eps)) - 1.f) / (2.f * eps);
-  const float mag = t * t - 1.f;
+  // same operation order as the torch expression (muzero_model.py:589-590), one rounding per op:
+  // the sqrt(1 + small) - 1 cancellation amplifies a 1-ulp change ~1e-5 relative, so do not fuse.
+  const float inner = __fadd_rn(1.f, __fmul_rn(0.004f, __fadd_rn(__fadd_rn(fabsf(y), 1.f), 0.001f)));
+  const float t = __fdiv_rn(__fsub_rn(__fsqrt_rn(inner), 1.f), 0.002f);
+  const float mag = __fsub_rn(__fmul_rn(t, t), 1.f);
   return y > 0.f ? mag : (y < 0.f ? -mag : 0.f);
 }
 

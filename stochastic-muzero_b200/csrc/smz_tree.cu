@@ -15,54 +15,70 @@
 
 namespace {
 
+#define FULL 0xffffffffu
+
+// Every kernel below keeps all 32 lanes of a warp converged: loops run for the warp-wide maximum trip
+// count and per-group work is predicated, so every shuffle / ballot is a full-mask, constant-mask
+// instruction on sub-warp segments of width G (no mask matching, no dependence on independent
+// thread scheduling).  Trees beyond n_trees keep their lanes alive with `alive == false`.
 template <int G>
 struct Group {
   int lane, gl, gbase;
-  unsigned gmask;
   __device__ Group() {
     lane = threadIdx.x & 31;
     gl = lane & (G - 1);
     gbase = lane & ~(G - 1);
-    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   }
   template <typename T>
-  __device__ T bcast(T v, int src) const { return __shfl_sync(gmask, v, gbase + src); }
+  __device__ T bcast(T v, int src) const { return __shfl_sync(FULL, v, src, G); }
   __device__ unsigned ballot(bool p) const {
-    unsigned b = __ballot_sync(gmask, p);
+    unsigned b = __ballot_sync(FULL, p);
     return (G == 32) ? b : ((b >> gbase) & ((1u << G) - 1u));
   }
 };
 
-// numpy float32 add.reduce over n values held one per lane: pairwise summation with an 8-way
-// unrolled block (n >= 8) or a plain loop from 0.f (n < 8) — numpy/_core/src/umath/loops_utils.h.src.
+// numpy float32 add.reduce over n values held one per lane (n may differ between the groups of a
+// warp): pairwise summation with an 8-way unrolled block (n >= 8) or a plain loop from 0.f (n < 8)
+// — numpy/_core/src/umath/loops_utils.h.src.  Trip counts are compile-time (G), adds are predicated.
 template <int G>
 __device__ float np_sum_f32(const Group<G>& g, float a, int n) {
-  if (G < 8 || n < 8) {
-    float r = 0.f;
-    for (int i = 0; i < n; ++i) r = __fadd_rn(r, g.bcast(a, i));
-    return r;
+  float seq = 0.f;
+#pragma unroll
+  for (int i = 0; i < (G < 7 ? G : 7); ++i) {
+    const float v = g.bcast(a, i);
+    if (i < n) seq = __fadd_rn(seq, v);
   }
+  if (G < 8) return seq;
   float r[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = g.bcast(a, j);
-  int i = 8;
-  for (; i < n - (n % 8); i += 8) {
+  for (int j = 0; j < 8; ++j) r[j] = g.bcast(a, j & (G - 1));
+  const int nb = n - (n % 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], g.bcast(a, (i + j) & (G - 1)));
+  for (int i = 8; i + 8 <= G; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = g.bcast(a, (i + j) & (G - 1));
+      if (i < nb) r[j] = __fadd_rn(r[j], v);
+    }
   }
   float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
                         __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __fadd_rn(res, g.bcast(a, i));
-  return res;
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const float v = g.bcast(a, (nb + t) & (G - 1));
+    if (nb + t < n) res = __fadd_rn(res, v);
+  }
+  return n < 8 ? seq : res;
 }
 
 // cdf of RandomState.choice: float64 cumsum of p (sequential), divided by the last entry.
-// Every lane i < n returns cdf[i]; lanes >= n return 2.0 (never <= u).
+// Every lane i < n returns cdf[i]; lanes >= n return 2.0 (never <= u).  Lanes >= n must pass p = 0.
 template <int G>
 __device__ double choice_cdf(const Group<G>& g, double p, int n) {
   double acc = 0.0, mine = 0.0;
-  for (int i = 0; i < n; ++i) {
-    acc = __dadd_rn(acc, g.bcast(p, i));
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    acc = __dadd_rn(acc, g.bcast(p, i));     // + 0.0 beyond n leaves acc unchanged
     if (g.gl == i) mine = acc;
   }
   return (g.gl < n) ? __ddiv_rn(mine, acc) : 2.0;
@@ -71,33 +87,36 @@ __device__ double choice_cdf(const Group<G>& g, double p, int n) {
 // (policy + 1e-12) / sum in float32 (mcts.py:205-206, :291-292); lanes >= n hold 0.
 template <int G>
 __device__ float normalise_policy(const Group<G>& g, float pol, int n) {
-  float p = (g.gl < n) ? __fadd_rn(pol, 1e-12f) : 0.f;
-  float s = np_sum_f32(g, p, n);
+  const float p = (g.gl < n) ? __fadd_rn(pol, 1e-12f) : 0.f;
+  const float s = np_sum_f32(g, p, n);
   return (g.gl < n) ? __fdiv_rn(p, s) : 0.f;
 }
 
 // np.random.choice(n, bound, p=p, replace=False): returns the bit set of chosen indices and advances
 // the tree's uniform cursor by the number of draws numpy would have consumed.
 template <int G>
-__device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, int tree, float p32,
+__device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, bool alive, int tree, float p32,
                                                int n, int bound, int& cursor) {
   unsigned found = 0;
-  int nf = 0;
-  const double pd = (double)p32;
-  for (int round = 0; nf < bound; ++round) {
+  int nf = alive ? 0 : bound;
+  const double pd = (g.gl < n) ? (double)p32 : 0.0;
+  for (int round = 0; __any_sync(FULL, nf < bound); ++round) {
     if (round > 2 * SMZ_MAX_POLICY) {   // NaN / degenerate policy: numpy would raise; do not hang
-      *a.error_flag = 2;
-      for (int i = 0; i < n && nf < bound; ++i)
-        if (!((found >> i) & 1u)) { found |= 1u << i; ++nf; }
+      if (nf < bound) {
+        *a.error_flag = 2;
+        for (int i = 0; i < n && nf < bound; ++i)
+          if (!((found >> i) & 1u)) { found |= 1u << i; ++nf; }
+      }
       break;
     }
-    const int m = bound - nf;
+    const int m = bound - nf;                    // 0 for groups that are done
     const double c = choice_cdf(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n);
-    for (int j = 0; j < m; ++j) {
-      const double u = smz_uniform(a, tree, cursor + j);
+    for (int j = 0; __any_sync(FULL, j < m); ++j) {
+      const bool on = j < m;
+      const double u = on ? smz_uniform(a, tree, cursor + j) : 0.0;
       int idx = __popc(g.ballot(c <= u));
       idx = idx < n ? idx : n - 1;
-      if (!((found >> idx) & 1u)) { found |= 1u << idx; ++nf; }
+      if (on && !((found >> idx) & 1u)) { found |= 1u << idx; ++nf; }
     }
     cursor += m;
   }
@@ -110,15 +129,17 @@ __global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__
                               const int* __restrict__ root_to_play, int train,
                               const double* __restrict__ dirichlet) {
   Group<G> g;
-  const int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (tree >= n_trees) return;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
   const size_t tb = (size_t)tree * a.M;
   const int n = a.A;
   int cursor = 0;
   const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
   const float p = normalise_policy(g, pol, n);
   // all A actions become children (ascending); the call still consumes its draws (T5)
-  choice_without_replacement(g, a, tree, p, n, n, cursor);
+  choice_without_replacement(g, a, alive, tree, p, n, n, cursor);
+  if (!alive) return;
   if (g.gl < n) {
     double prior = (double)p;
     if (train) {
@@ -146,8 +167,9 @@ template <int G>
 __global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_slot, int* __restrict__ o_action,
                          int* __restrict__ o_branch) {
   Group<G> g;
-  const int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (tree >= n_trees) return;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
   const size_t tb = (size_t)tree * a.M;
   int cursor = a.ucursor[tree];
   const float2 mm = a.minmax[tree];
@@ -156,30 +178,35 @@ __global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_s
 
   int depth = 0, cbase = 1, nch = a.A;
   int parent_visit = a.stat[tb].x;
-  if (g.gl == 0) path[0] = 0;
+  if (alive && g.gl == 0) path[0] = 0;
   int L = 1, child = 0, child_key = 0;
-  for (;;) {
-    const bool act = g.gl < nch;
+  bool going = alive;
+  while (__any_sync(FULL, going)) {
+    const bool act = going && g.gl < nch;
+    const bool chance = (depth >> 1) & 1;
     int4 st = make_int4(0, 0, 0, 0);
     int2 lk = make_int2(0, 0);
     if (act) { st = a.stat[tb + cbase + g.gl]; lk = a.link[tb + cbase + g.gl]; }
-    int pick;
-    if ((depth >> 1) & 1) {
+    int pick = 0;
+    if (__any_sync(FULL, going && chance)) {
       // chance node: sample a child from the smoothed priors (mcts.py:249-255, T9)
       const float p = __int_as_float(st.w);
       const float om = act ? __fadd_rn(__fsub_rn(1.f, p), 1e-12f) : 0.f;
       const float rem = fabsf(__fdiv_rn(np_sum_f32(g, om, nch), (float)nch));
       const float sh = act ? __fadd_rn(p, rem) : 0.f;
-      const float q = act ? __fdiv_rn(sh, np_sum_f32(g, sh, nch)) : 0.f;
+      const float tot = np_sum_f32(g, sh, nch);
+      const float q = act ? __fdiv_rn(sh, tot) : 0.f;
       const double c = choice_cdf(g, (double)q, nch);
-      const double u = smz_uniform(a, tree, cursor);
-      cursor += 1;
-      pick = __popc(g.ballot(c <= u));
-      pick = pick < nch ? pick : nch - 1;
-    } else {
+      const double u = (going && chance) ? smz_uniform(a, tree, cursor) : 0.0;
+      int pk = __popc(g.ballot(act && c <= u));
+      pk = pk < nch ? pk : nch - 1;
+      if (chance) { pick = pk; cursor += going ? 1 : 0; }
+    }
+    if (__any_sync(FULL, going && !chance)) {
       // decision node: argmax of ucb_score, one fresh uniform per child (mcts.py:235-243, T3/T5/T6)
       double score = -__longlong_as_double(0x7ff0000000000000LL);
-      if (act) {
+      int best = -1;
+      if (act && !chance) {
         const double prior = (depth == 0) ? a.root_prior[(size_t)tree * a.A + g.gl] : (double)__int_as_float(st.w);
         const double u = smz_uniform(a, tree, cursor + g.gl);
         const double pb_c = a.pbc[parent_visit];
@@ -193,31 +220,36 @@ __global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_s
         }
         const double noise = __dadd_rn(1e-7, __dmul_rn(2e-7 - 1e-7, u));
         score = __dadd_rn(__dadd_rn(ps, vs), noise);
+        best = g.gl;
       }
-      cursor += nch;
-      int best = act ? g.gl : -1;
 #pragma unroll
       for (int off = G / 2; off > 0; off >>= 1) {
-        const double os = __shfl_xor_sync(g.gmask, score, off);
-        const int ob = __shfl_xor_sync(g.gmask, best, off);
+        const double os = __shfl_xor_sync(FULL, score, off, G);
+        const int ob = __shfl_xor_sync(FULL, best, off, G);
         if (os > score || (os == score && ob > best)) { score = os; best = ob; }
       }
-      pick = best < 0 ? 0 : best;
+      if (!chance) { pick = best < 0 ? 0 : best; cursor += going ? nch : 0; }
     }
     const int child_visit = g.bcast(st.x, pick);
     const int child_cb = g.bcast(lk.x, pick);
-    child_key = g.bcast(lk.y, pick);
-    child = cbase + pick;
-    if (g.gl == 0) path[L] = child;
-    ++L;
-    if (child_cb == 0 || L >= a.path_stride) break;
-    // the child (depth+1) was expanded through the dynamics pair iff this node is a chance node (T2)
-    nch = ((depth >> 1) & 1) ? a.Kd : a.Kc;
-    parent_visit = child_visit;
-    cbase = child_cb;
-    ++depth;
+    const int key = g.bcast(lk.y, pick);
+    if (going) {
+      child = cbase + pick;
+      child_key = key;
+      if (g.gl == 0) path[L] = child;
+      ++L;
+      if (child_cb == 0 || L >= a.path_stride) {
+        going = false;
+      } else {
+        // the child (depth+1) was expanded through the dynamics pair iff this node is a chance node (T2)
+        nch = chance ? a.Kd : a.Kc;
+        parent_visit = child_visit;
+        cbase = child_cb;
+        ++depth;
+      }
+    }
   }
-  if (g.gl == 0) {
+  if (alive && g.gl == 0) {
     const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
     const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
     a.leaf_node[tree] = child;
@@ -240,12 +272,13 @@ template <int G>
 __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* __restrict__ policy, int pstride,
                                 const float* __restrict__ value, const float* __restrict__ reward) {
   Group<G> g;
-  const int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (tree >= n_trees) return;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
   const size_t tb = (size_t)tree * a.M;
   const int leaf = a.leaf_node[tree];
   const int branch = a.leaf_branch[tree];
-  const int L = a.path_len[tree];
+  const int L = alive ? a.path_len[tree] : 0;
   int cursor = a.ucursor[tree];
   const int* path = a.path + (size_t)tree * a.path_stride;
 
@@ -254,16 +287,16 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
   const int bound = min(a.K, n);
   const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
   const float p = normalise_policy(g, pol, n);
-  const unsigned found = choice_without_replacement(g, a, tree, p, n, bound, cursor);
+  const unsigned found = choice_without_replacement(g, a, alive, tree, p, n, bound, cursor);
   const int cb = 1 + a.A + sim * a.Kmax;
-  if (g.gl < n && ((found >> g.gl) & 1u)) {
+  if (alive && g.gl < n && ((found >> g.gl) & 1u)) {
     const int r = __popc(found & ((1u << g.gl) - 1u));
     a.stat[tb + cb + r] = make_int4(0, 0, 0, __float_as_int(p));
     a.link[tb + cb + r] = make_int2(0, g.gl);
   }
   float v = value[tree];
   const float rew = branch ? reward[tree] : 0.f;
-  if (g.gl == 0) {
+  if (alive && g.gl == 0) {
     a.link[tb + leaf].x = cb;
     a.ucursor[tree] = cursor;
     if (a.rec_policy) {
@@ -279,7 +312,9 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
   // float32 recurrence (mul then add, two roundings) carried through shuffles
   const signed char* sign = a.sign + (size_t)a.root_to_play[tree] * (a.N + 2);
   float2 mm = a.minmax[tree];
-  const int n_chunks = (L + G - 1) / G;
+  int n_chunks = (L + G - 1) / G;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n_chunks = max(n_chunks, __shfl_xor_sync(FULL, n_chunks, off));
   for (int chunk = n_chunks - 1; chunk >= 0; --chunk) {
     const int l = chunk * G + g.gl;
     const bool valid = l < L;
@@ -292,11 +327,13 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
     }
     const float r = __int_as_float(st.z);
     float myv = 0.f;
-    const int hi = min(L, (chunk + 1) * G) - 1;
-    for (int i = hi; i >= chunk * G; --i) {
-      if (l == i) myv = v;
-      const float ri = g.bcast(r, i - chunk * G);
-      v = __fadd_rn(ri, __fmul_rn(a.discount, v));
+#pragma unroll
+    for (int t = G - 1; t >= 0; --t) {
+      const float ri = g.bcast(r, t);
+      if (chunk * G + t < L) {
+        if (g.gl == t) myv = v;
+        v = __fadd_rn(ri, __fmul_rn(a.discount, v));
+      }
     }
     if (valid) {
       const float vs = __fadd_rn(__int_as_float(st.y), sign[l] > 0 ? myv : -myv);
@@ -310,10 +347,10 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
   }
 #pragma unroll
   for (int off = G / 2; off > 0; off >>= 1) {
-    mm.x = fminf(mm.x, __shfl_xor_sync(g.gmask, mm.x, off));
-    mm.y = fmaxf(mm.y, __shfl_xor_sync(g.gmask, mm.y, off));
+    mm.x = fminf(mm.x, __shfl_xor_sync(FULL, mm.x, off, G));
+    mm.y = fmaxf(mm.y, __shfl_xor_sync(FULL, mm.y, off, G));
   }
-  if (g.gl == 0) a.minmax[tree] = mm;
+  if (alive && g.gl == 0) a.minmax[tree] = mm;
 }
 
 // ------------------------------------------------------------------------------------------------
