@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from .engine import SearchEngine, _is_chance
-from .weights import pack_weights, shape_of, weights_version
+from .weights import PackedModel, pack_weights, shape_of, weights_version
 
 
 class Node(object):
@@ -265,6 +265,8 @@ class Monte_carlo_tree_search():
 
     @staticmethod
     def _is_fusable(model):
+        if isinstance(model, PackedModel):
+            return True
         return getattr(model, "model_structure", None) == "mlp_model" and all(
             hasattr(model, f"{n}_function") for n in ("representation", "prediction", "afterstate_prediction",
                                                       "afterstate_dynamics", "dynamics", "encoder"))

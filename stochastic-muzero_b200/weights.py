@@ -71,6 +71,22 @@ def random_blob(shape: ModelShape, seed: int = 0, std: float = 1.0 / 137.035999)
     return (np.random.default_rng(seed).standard_normal(total) * std).astype(np.float32)
 
 
+class PackedModel:
+    """Weights already in hand-off form (blob + shape): accepted by ``run_batch`` / ``run`` wherever a
+    reference ``Muzero`` is.  ``bump()`` after replacing ``blob`` in place to make engines re-upload."""
+    model_structure = "mlp_model"
+
+    def __init__(self, blob, shape: ModelShape):
+        _, total = blob_layout(shape)
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        if blob.size != total:
+            raise ValueError(f"blob has {blob.size} floats, shape needs {total}")
+        self.blob, self.shape, self.version = blob, shape, 0
+
+    def bump(self):
+        self.version += 1
+
+
 def _unwrap(module):
     """muzero_model.py:360-367 wraps the modules in DataParallel when several GPUs are visible."""
     return module.module if module.__class__.__name__ == "DataParallel" else module
@@ -83,6 +99,8 @@ def _linears(sequential):
 
 def shape_of(model) -> ModelShape:
     """ModelShape of a reference-style ``Muzero`` (attributes set in muzero_model.py __init__)."""
+    if isinstance(model, PackedModel):
+        return model.shape
     rep = _linears(_unwrap(model.representation_function).state_norm)
     pol = _linears(_unwrap(model.prediction_function).policy)
     apol = _linears(_unwrap(model.afterstate_prediction_function).policy)
@@ -95,6 +113,8 @@ def shape_of(model) -> ModelShape:
 
 def weights_version(model) -> tuple:
     """Cheap change detector: torch bumps ``_version`` on every in-place update (optimizer steps)."""
+    if isinstance(model, PackedModel):
+        return (id(model), model.version)
     vers = []
     for name in ("representation", "prediction", "afterstate_dynamics", "afterstate_prediction", "dynamics",
                  "encoder"):
@@ -107,6 +127,8 @@ def weights_version(model) -> tuple:
 def pack_weights(model) -> Tuple[np.ndarray, ModelShape]:
     """Walk the six modules of a reference ``Muzero`` (or any object exposing the same six
     ``*_function`` Sequential stacks) and return (blob, shape)."""
+    if isinstance(model, PackedModel):
+        return model.blob, model.shape
     shape = shape_of(model)
     L = shape.num_hidden_layers
     parts = []
