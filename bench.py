@@ -147,7 +147,7 @@ def main():
     B, N = args.trees, args.sims
     net = args.net
     if net == "auto":
-        net = os.environ.get("SMZ_DEFAULT_NET", "fp32")
+        net = os.environ.get("SMZ_DEFAULT_NET", "bf16")
     eng = SearchEngine(search, shape.action_dim, shape.chance_dim, max_trees=B, model_shape=shape, net=net,
                        rng="philox", seed=20240 + rank, tree_id_offset=rank * B, device=local)
 
@@ -235,7 +235,7 @@ def main():
     depth = stats["mean_leaf_depth"]
     tb = tree_bytes_per_sim(depth, SEARCH["maxium_action_sample"], DIMS["state_dim"]) * B
     achieved_gbs = tb / ((t_sel + t_exp) * 1e-3) / 1e9
-    roofline = {"kernel": "network step (k_net_sim, %s)" % net, "bound": "tensor", "achieved": achieved_tf,
+    roofline = {"kernel": "network step (%s)" % ("k_bf16_chain, tcgen05 bf16" if net == "bf16" else "k_net_sim, fp32 CUDA cores"), "bound": "tensor", "achieved": achieved_tf,
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
                 "peak_source": which + ", sustained bf16", "avg_launch_us": 1e3 * t_net,
                 "algorithmic_flops_per_launch": flops_launch,

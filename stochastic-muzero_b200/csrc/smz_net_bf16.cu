@@ -1,18 +1,616 @@
-// smz_net_bf16.cu — placeholder until the tcgen05 path lands: creating a BF16 engine fails loudly.
+// smz_net_bf16.cu — the per-simulation network step on the 5th-generation tensor cores (sm_100a).
+//
+// One CTA (128 threads = 128 TMEM lanes = 128 leaves) pushes a tile of leaves through a whole
+// network pair — e.g. Dynamics (mlp:167-206) then Prediction (mlp:47-83): 2*(L+2) dependent GEMM
+// layers — without leaving the SM:
+//   * the layer's weight tile (B operand, bf16, <= 32 KB, pre-laid-out in the UMMA canonical K-major
+//     no-swizzle form by k_pack_bf16) streams global -> shared with cp.async.bulk (TMA bulk copy,
+//     SASS UBLKCP) into a 2-deep ring, completion on an mbarrier, two layers ahead of the math;
+//   * one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16 per instruction),
+//     A = the activations in shared memory (bf16, written by the previous epilogue in canonical
+//     layout), D = fp32 accumulators in TMEM; tcgen05.commit signals an mbarrier;
+//   * the epilogue is row-per-thread: tcgen05.ld 32 lanes x 32 columns per warp, bias + ELU in fp32,
+//     pack to bf16 and store straight into the next layer's A operand (conflict-free 16-byte stores);
+//     the head layers finish scale_to_bound_action (mlp:349-357), softmax on the policy (:837) and
+//     inverse_transform_with_support (muzero_model.py:575-591) thread-locally — no shuffles.
+// The one-hot action / chance code (muzero_model.py:496-509) is folded into the first GEMM as 16 or
+// 32 extra K columns holding a single 1.0.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/smz.h"
 #include "smz_net_bf16.h"
 
-struct SmzBf16Image { int unused; };
+namespace {
 
-int smz_bf16_create(const SmzNetShape&, const SmzArena&, SmzBf16Image**, char* err, size_t err_len) {
-  snprintf(err, err_len, "SMZ_NET_BF16 is not available in this build");
-  return SMZ_E_STATE;
+constexpr int TM = 128;                 // rows (leaves) per CTA == MMA M
+constexpr int TN = 128;                 // MMA N (all layers padded to 128 output channels)
+constexpr int KMAX = 128;               // widest K
+constexpr int MAXL = 24;                // layers per chain: 2 * (L + 2), L <= 10
+constexpr int A_BYTES = TM * KMAX * 2;  // 32 KB activation operand
+constexpr int W_BYTES = TN * KMAX * 2;  // 32 KB weight operand (one ring slot)
+constexpr int CHUNK_A = TM * 16;        // bytes between K-chunks (8 bf16) of the A operand: LBO
+constexpr int CHUNK_W = TN * 16;        // same for the B operand
+constexpr int POL_OFF = 64;             // column of the second head inside a head tile
+
+enum LayerKind { LK_HIDDEN = 0, LK_STATE = 1, LK_STATE_REWARD = 2, LK_PRED = 3, LK_CODE = 4 };
+enum InputKind { IN_GATHER = 0, IN_OBS = 1, IN_ROWS = 2 };
+
+struct LayerRef {
+  const __nv_bfloat16* w;   // [K/8][128][8] canonical image
+  int K;                    // multiple of 16
+  int kind;
+};
+
+struct Chain {
+  LayerRef layer[MAXL];
+  const float* bias;        // [n_layers][128]
+  int n_layers;
+  int n_policy;             // width of the policy / code head of this chain
+  int kin;                  // K of the first layer
+  int onehot_pad;           // 0, 16 or 32 one-hot columns after the 64 state columns
+};
+
+struct Job {
+  int input_kind;
+  int n_rows;               // rows when not compacted
+  const float* in;          // IN_OBS: [n][obs]; IN_ROWS: [n][64]
+  const int* idx;           // IN_ROWS: action / code per row (or null)
+  int obs;                  // IN_OBS width
+  float* hidden_dst;        // [index][64] or null
+  float* policy_dst;        // [index][pstride] or null
+  float* value_dst;
+  float* reward_dst;
+  int* code_dst;
+  int pstride;
+  int S;
+};
+
+struct Smem {
+  alignas(1024) unsigned char a[A_BYTES];
+  alignas(1024) unsigned char w[2][W_BYTES];
+  float bias[MAXL][TN];
+  unsigned long long wbar[2];
+  unsigned long long mbar;
+  unsigned long long bbar;
+  unsigned int tmem_base;
+  int index[TM];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
 }
-void smz_bf16_destroy(SmzBf16Image*) {}
-int smz_bf16_pack(SmzBf16Image*, const SmzNetShape&, const float*, cudaStream_t, char*, size_t) { return SMZ_E_STATE; }
-void smz_bf16_root(SmzBf16Image*, const SmzArena&, const SmzNetShape&, int, const float*, cudaStream_t) {}
-void smz_bf16_sim(SmzBf16Image*, const SmzArena&, const SmzNetShape&, int, int, cudaStream_t) {}
-void smz_bf16_eval(SmzBf16Image*, const SmzNetShape&, int, int, const float*, const int*, float*, float*, float*,
-                   float*, int*, int, cudaStream_t) {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error becomes a trap (CUDA error), never a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = s32(bar);
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("smz bf16: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+               "l"(src), "r"(bytes), "r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+  // version=1 [46,48), layout_type SWIZZLE_NONE=0 [61,64)
+  return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | ((unsigned long long)(lbo_bytes >> 4) << 16) |
+         ((unsigned long long)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr unsigned IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
+
+__device__ __forceinline__ void umma(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <-> lane base+t)
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&p);
+}
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
+// store 8 consecutive K values of row r (already bf16-packed) into the canonical A operand
+__device__ __forceinline__ void a_store(unsigned char* a, int r, int kchunk, uint4 v) {
+  *reinterpret_cast<uint4*>(a + kchunk * CHUNK_A + r * 16) = v;
+}
+
+// inverse_transform_with_support on S logits held in registers (muzero_model.py:575-591)
+__device__ __forceinline__ float support_scalar(const float* x, int S) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) if (i < S) m = fmaxf(m, x[i]);
+  float z = 0.f, y = 0.f;
+  const int half = S / 2;
+#pragma unroll
+  for (int i = 0; i < 64; ++i)
+    if (i < S) {
+      const float e = __expf(x[i] - m);
+      z += e;
+      y += (float)(i - half) * e;
+    }
+  y /= z;
+  const float inner = __fadd_rn(1.f, __fmul_rn(0.004f, __fadd_rn(__fadd_rn(fabsf(y), 1.f), 0.001f)));
+  const float t = __fdiv_rn(__fsub_rn(__fsqrt_rn(inner), 1.f), 0.002f);
+  const float mag = __fsub_rn(__fmul_rn(t, t), 1.f);
+  return y > 0.f ? mag : (y < 0.f ? -mag : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused chain kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TM, 1)
+k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // ---- which rows does this CTA own? ------------------------------------------------------------
+  int tile = blockIdx.x, branch = 0, count = job.n_rows;
+  if (job.input_kind == IN_GATHER) {
+    const int n0 = a.branch_count[sim * 2 + 0], n1 = a.branch_count[sim * 2 + 1];
+    const int t0 = (n0 + TM - 1) / TM, t1 = (n1 + TM - 1) / TM;
+    if (tile < t0) { branch = 0; count = n0; }
+    else if (tile < t0 + t1) { branch = 1; count = n1; tile -= t0; }
+    else return;
+  } else if (tile * TM >= count) {
+    return;
+  }
+  const Chain& ch = branch ? chain1 : chain0;
+  const int row = tile * TM + tid;
+  const bool valid = row < count;
+
+  // ---- barriers, TMEM, first weight tiles ---------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(&sm.wbar[0], 1);
+    mbar_init(&sm.wbar[1], 1);
+    mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.bbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = sm.tmem_base;
+  auto load_weights = [&](int l) {
+    const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[l & 1], bytes);
+    bulk_g2s(sm.w[l & 1], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
+  };
+  if (tid == 0) {
+    const unsigned bbytes = (unsigned)ch.n_layers * TN * 4;
+    mbar_expect_tx(&sm.bbar, bbytes);
+    bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
+    load_weights(0);
+    if (ch.n_layers > 1) load_weights(1);
+  }
+
+  // ---- stage the first A operand: one row per thread, bf16, canonical K-major layout ---------------
+  int index = -1;      // tree id (gather) or caller row
+  {
+    uint4 z4 = make_uint4(0, 0, 0, 0);
+    if (job.input_kind == IN_OBS) {
+      index = valid ? row : -1;
+      for (int kc = 0; kc < ch.kin / 8; ++kc) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = kc * 8 + j;
+          v[j] = (valid && c < job.obs) ? job.in[(size_t)row * job.obs + c] : 0.f;
+        }
+        a_store(sm.a, tid, kc, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+      }
+    } else {
+      const float* src = nullptr;
+      int act = -1;
+      if (valid) {
+        if (job.input_kind == IN_GATHER) {
+          index = a.rows[(size_t)branch * a.B + row];
+          src = a.hidden + ((size_t)a.leaf_slot[index] * a.B + index) * SMZ_SP;
+          act = a.leaf_action[index];
+        } else {
+          index = row;
+          src = job.in + (size_t)row * SMZ_SP;
+          act = job.idx ? job.idx[row] : -1;
+        }
+      }
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        uint4 o = z4;
+        if (valid) {
+          const float4 lo = *reinterpret_cast<const float4*>(src + kc * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(src + kc * 8 + 4);
+          o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+        }
+        a_store(sm.a, tid, kc, o);
+      }
+      for (int kc = 0; kc < ch.onehot_pad / 8; ++kc) {   // one-hot columns 64 + act
+        unsigned w4[4] = {0, 0, 0, 0};
+        if (valid && act >= kc * 8 && act < kc * 8 + 8) {
+          const int j = act - kc * 8;
+          w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+        }
+        a_store(sm.a, tid, 8 + kc, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+      }
+    }
+  }
+  sm.index[tid] = index;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  mbar_wait(&sm.bbar, 0);
+
+  const unsigned lane_taddr = tmem + ((unsigned)(warp * 32) << 16);
+  const int S = job.S;
+
+  // ---- the layer loop ---------------------------------------------------------------------------------
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const int K = ch.layer[l].K, kind = ch.layer[l].kind;
+    if (tid == 0) {
+      mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
+      tc_fence_after();
+      const unsigned a_addr = s32(sm.a), w_addr = s32(sm.w[l & 1]);
+      for (int k = 0; k < K / 16; ++k)
+        umma(tmem, umma_desc(a_addr + k * 2 * CHUNK_A, CHUNK_A, 128), umma_desc(w_addr + k * 2 * CHUNK_W, CHUNK_W, 128),
+             k > 0 ? 1u : 0u);
+      umma_commit(&sm.mbar);
+    }
+    mbar_wait(&sm.mbar, l & 1);
+    tc_fence_after();
+    if (tid == 0 && l + 2 < ch.n_layers) load_weights(l + 2);   // ring slot l&1 is free again
+    const float* bias = sm.bias[l];
+
+    if (kind == LK_HIDDEN) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + bias[c0 + j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          a_store(sm.a, tid, (c0 >> 3) + q,
+                  make_uint4(pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7])));
+      }
+    } else if (kind == LK_STATE || kind == LK_STATE_REWARD) {
+      // scale_to_bound_action over the S state logits of this row; fp32 copy to HBM, bf16 copy = next A
+      float x[64];
+      tmem_ld32(lane_taddr, x);
+      tmem_ld32(lane_taddr + 32, x + 32);
+      float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        x[i] += bias[i];
+        if (i < S) { lo = fminf(lo, x[i]); hi = fmaxf(hi, x[i]); }
+      }
+      float scale = hi - lo;
+      if (scale < 1e-5f) scale += 1e-5f;
+      const float inv = 1.f / scale;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] = i < S ? (x[i] - lo) * inv : 0.f;
+      if (index >= 0 && job.hidden_dst) {
+        float4* dst = reinterpret_cast<float4*>(job.hidden_dst + (size_t)index * SMZ_SP);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) dst[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        a_store(sm.a, tid, q, make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                         pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
+      if (kind == LK_STATE_REWARD) {
+        tmem_ld32(lane_taddr + POL_OFF, x);
+        tmem_ld32(lane_taddr + POL_OFF + 32, x + 32);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) x[i] += bias[POL_OFF + i];
+        const float r = support_scalar(x, S);
+        if (index >= 0 && job.reward_dst) job.reward_dst[index] = r;
+      }
+    } else if (kind == LK_PRED) {
+      float x[64];
+      tmem_ld32(lane_taddr, x);
+      tmem_ld32(lane_taddr + 32, x + 32);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] += bias[i];
+      const float val = support_scalar(x, S);
+      if (index >= 0 && job.value_dst) job.value_dst[index] = val;
+      tmem_ld32(lane_taddr + POL_OFF, x);
+      const int n = ch.n_policy;
+      float m = -INFINITY, z = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        x[i] += bias[POL_OFF + i];
+        if (i < n) m = fmaxf(m, x[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        x[i] = i < n ? __expf(x[i] - m) : 0.f;
+        z += x[i];
+      }
+      if (index >= 0 && job.policy_dst) {
+        float* dst = job.policy_dst + (size_t)index * job.pstride;
+        const float inv = 1.f / z;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < n) dst[i] = x[i] * inv;
+      }
+    } else {   // LK_CODE: Encoder (mlp:209-250) softmax over C code logits + argmax
+      float x[32];
+      tmem_ld32(lane_taddr, x);
+      const int n = ch.n_policy;
+      float m = -INFINITY, z = 0.f;
+      int best = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        x[i] += bias[i];
+        if (i < n && x[i] > m) { m = x[i]; best = i; }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        x[i] = i < n ? __expf(x[i] - m) : 0.f;
+        z += x[i];
+      }
+      if (index >= 0) {
+        if (job.policy_dst)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < n) job.policy_dst[(size_t)index * job.pstride + i] = x[i] / z;
+        if (job.code_dst) job.code_dst[index] = best;
+      }
+    }
+    // make the new A operand visible to the tensor core (async proxy) and retire the TMEM reads
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight image: torch Linear W[out][in] (fp32 blob) -> bf16 canonical B operand [K/8][128][8]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_bf16(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int n_rows, int in_stride,
+                            int seg0, int seg1_dst, int seg1_src, int seg1_n, int dst_n0) {
+  // dst k in [0, seg0) <- src column k;  dst k in [seg1_dst, seg1_dst + seg1_n) <- src column seg1_src + (k - seg1_dst)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = seg0 + seg1_n;
+  if (i >= n_rows * per_row) return;
+  const int n = i / per_row, j = i % per_row;
+  const int k = j < seg0 ? j : seg1_dst + (j - seg0);
+  const int c = j < seg0 ? j : seg1_src + (j - seg0);
+  dst[((size_t)(k >> 3) * TN + dst_n0 + n) * 8 + (k & 7)] = __float2bfloat16_rn(src[(size_t)n * in_stride + c]);
+}
+__global__ void k_copy_f32(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct NetImg {
+  __nv_bfloat16 *in_w, *mid_w, *head_w;
+  float *in_b, *mid_b, *head_b;   // 128 floats each
+  int kin, head_kind, n_policy, onehot_pad;
+};
+
+struct SmzBf16Image {
+  SmzNetShape sh;
+  NetImg net[6];          // repr, pred, adyn, apred, dyn, enc
+  Chain chain_after, chain_dyn, chain_root, chain_single[6];
+  float* bias_pool;       // device: per chain [n_layers][128]
+  unsigned char* pool;    // device: all images
+  size_t pool_bytes;
+  int smem_bytes;
+};
+
+static int round16(int v) { return (v + 15) / 16 * 16; }
+
+int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, char* err, size_t err_len) {
+  if (2 * (sh.L + 2) > MAXL) {
+    snprintf(err, err_len, "SMZ_NET_BF16: number_of_hidden_layer %d exceeds %d", sh.L, MAXL / 2 - 2);
+    return SMZ_E_CAPACITY;
+  }
+  if (sh.OH > 32) {
+    snprintf(err, err_len, "SMZ_NET_BF16: one-hot width %d exceeds 32", sh.OH);
+    return SMZ_E_CAPACITY;
+  }
+  SmzBf16Image* im = new SmzBf16Image();
+  memset(im, 0, sizeof(*im));
+  im->sh = sh;
+  const int ohp = round16(sh.OH);
+  const int kin[6] = {round16(sh.obs), 64, 64 + ohp, 64, 64 + ohp, round16(sh.obs)};
+  const int kind[6] = {LK_STATE, LK_PRED, LK_STATE, LK_PRED, LK_STATE_REWARD, LK_CODE};
+  const int npol[6] = {0, sh.A, 0, sh.C, 0, sh.C};
+  // pool: per net in (kin x 128) + mid (128 x 128) + head (128 x 128) bf16, + 3 x 128 fp32 biases; then chain biases
+  size_t bytes = 0;
+  for (int i = 0; i < 6; ++i) bytes += (size_t)(kin[i] + 2 * KMAX) * TN * 2 + 3 * TN * 4;
+  const size_t chain_bias_floats = (size_t)(3 + 6) * MAXL * TN;
+  bytes += chain_bias_floats * 4;
+  if (cudaMalloc(&im->pool, bytes) != cudaSuccess) {
+    snprintf(err, err_len, "SMZ_NET_BF16: cudaMalloc of the weight image failed");
+    delete im;
+    return SMZ_E_CUDA;
+  }
+  im->pool_bytes = bytes;
+  unsigned char* p = im->pool;
+  for (int i = 0; i < 6; ++i) {
+    NetImg& n = im->net[i];
+    n.kin = kin[i]; n.head_kind = kind[i]; n.n_policy = npol[i]; n.onehot_pad = (i == 2 || i == 4) ? ohp : 0;
+    n.in_w = (__nv_bfloat16*)p; p += (size_t)kin[i] * TN * 2;
+    n.mid_w = (__nv_bfloat16*)p; p += (size_t)KMAX * TN * 2;
+    n.head_w = (__nv_bfloat16*)p; p += (size_t)KMAX * TN * 2;
+    n.in_b = (float*)p; p += TN * 4;
+    n.mid_b = (float*)p; p += TN * 4;
+    n.head_b = (float*)p; p += TN * 4;
+  }
+  im->bias_pool = (float*)p;
+  im->smem_bytes = (int)sizeof(Smem) + 1024;
+  cudaFuncSetAttribute((const void*)k_bf16_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  *out = im;
+  return SMZ_OK;
+}
+
+void smz_bf16_destroy(SmzBf16Image* im) {
+  if (!im) return;
+  cudaFree(im->pool);
+  delete im;
+}
+
+static void build_chain(SmzBf16Image* im, Chain* ch, const int* nets, int n_nets, float* bias_dst, cudaStream_t s) {
+  memset(ch, 0, sizeof(*ch));
+  int l = 0;
+  for (int t = 0; t < n_nets; ++t) {
+    const NetImg& n = im->net[nets[t]];
+    auto add = [&](const __nv_bfloat16* w, const float* b, int K, int kind) {
+      ch->layer[l].w = w; ch->layer[l].K = K; ch->layer[l].kind = kind;
+      k_copy_f32<<<1, TN, 0, s>>>(bias_dst + (size_t)l * TN, b, TN);
+      ++l;
+    };
+    add(n.in_w, n.in_b, n.kin, LK_HIDDEN);
+    for (int i = 0; i < im->sh.L; ++i) add(n.mid_w, n.mid_b, KMAX, LK_HIDDEN);
+    add(n.head_w, n.head_b, KMAX, n.head_kind);
+    if (n.n_policy) ch->n_policy = n.n_policy;
+  }
+  ch->n_layers = l;
+  ch->bias = bias_dst;
+  ch->kin = im->net[nets[0]].kin;
+  ch->onehot_pad = im->net[nets[0]].onehot_pad;
+}
+
+int smz_bf16_pack(SmzBf16Image* im, const SmzNetShape& sh, const float* blob, cudaStream_t s, char* err, size_t err_len) {
+  if (cudaMemsetAsync(im->pool, 0, im->pool_bytes, s) != cudaSuccess) {
+    snprintf(err, err_len, "SMZ_NET_BF16: memset failed");
+    return SMZ_E_CUDA;
+  }
+  const int S = sh.S, H = sh.H, A = sh.A, C = sh.C, OH = sh.OH;
+  size_t off = 0;
+  auto pack = [&](__nv_bfloat16* dst, int n_rows, int in_stride, int seg0, int seg1_dst, int seg1_src, int seg1_n, int dst_n0) {
+    const int n = n_rows * (seg0 + seg1_n);
+    k_pack_bf16<<<(n + 255) / 256, 256, 0, s>>>(dst, blob + off, n_rows, in_stride, seg0, seg1_dst, seg1_src, seg1_n, dst_n0);
+    off += (size_t)n_rows * in_stride;
+  };
+  auto vec = [&](float* dst, int n) {
+    k_copy_f32<<<1, 128, 0, s>>>(dst, blob + off, n);
+    off += n;
+  };
+  // blob order: repr, pred, adyn, apred, dyn, enc (stochastic-muzero_b200/weights.py)
+  const int in_dim[6] = {sh.obs, S, S + OH, S, S + OH, sh.obs};
+  const int order[6] = {0, 1, 2, 3, 4, 5};
+  for (int t = 0; t < 6; ++t) {
+    NetImg& n = im->net[order[t]];
+    const bool oh = (t == 2 || t == 4);
+    const int live = oh ? S : in_dim[t];
+    pack(n.in_w, H, in_dim[t], live, 64, S, oh ? OH : 0, 0);
+    vec(n.in_b, H);
+    if (sh.L > 0) { pack(n.mid_w, H, H, H, 0, 0, 0, 0); vec(n.mid_b, H); }
+    switch (t) {
+      case 0: pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  // repr: state
+      case 1: pack(n.head_w, A, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, A);                          // pred: policy,
+              pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  //       value
+      case 2: pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  // adyn: state
+      case 3: pack(n.head_w, C, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, C);
+              pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;
+      case 4: pack(n.head_w, S, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, S);                          // dyn: reward,
+              pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  //      state
+      case 5: pack(n.head_w, C, H, H, 0, 0, 0, 0); vec(n.head_b, C); break;                                  // enc: code
+    }
+  }
+  float* bp = im->bias_pool;
+  { const int nets[2] = {2, 3}; build_chain(im, &im->chain_after, nets, 2, bp, s); bp += MAXL * TN; }
+  { const int nets[2] = {4, 1}; build_chain(im, &im->chain_dyn, nets, 2, bp, s); bp += MAXL * TN; }
+  { const int nets[2] = {0, 1}; build_chain(im, &im->chain_root, nets, 2, bp, s); bp += MAXL * TN; }
+  for (int i = 0; i < 6; ++i) { const int nets[1] = {i}; build_chain(im, &im->chain_single[i], nets, 1, bp, s); bp += MAXL * TN; }
+  if (cudaGetLastError() != cudaSuccess) {
+    snprintf(err, err_len, "SMZ_NET_BF16: weight packing launch failed");
+    return SMZ_E_CUDA;
+  }
+  return SMZ_OK;
+}
+
+void smz_bf16_root(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, const float* obs, cudaStream_t s) {
+  Job job{};
+  job.input_kind = IN_OBS; job.n_rows = n_trees; job.in = obs; job.obs = sh.obs; job.S = sh.S;
+  job.hidden_dst = a.hidden; job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
+  k_bf16_chain<<<(n_trees + TM - 1) / TM, TM, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
+}
+
+void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, cudaStream_t s) {
+  Job job{};
+  job.input_kind = IN_GATHER; job.n_rows = n_trees; job.S = sh.S;
+  job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * SMZ_SP;
+  job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
+  k_bf16_chain<<<(n_trees + TM - 1) / TM + 1, TM, im->smem_bytes, s>>>(a, im->chain_after, im->chain_dyn, job, sim);
+}
+
+void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_rows, const float* in, const int* idx,
+                   float* hidden_out, float* policy_out, float* value_out, float* reward_out, int* code_out,
+                   int policy_stride, cudaStream_t s) {
+  Job job{};
+  job.input_kind = (which == 0 || which == 5) ? IN_OBS : IN_ROWS;
+  job.n_rows = n_rows; job.in = in; job.idx = idx; job.obs = sh.obs; job.S = sh.S;
+  job.hidden_dst = hidden_out; job.policy_dst = policy_out; job.value_dst = value_out; job.reward_dst = reward_out;
+  job.code_dst = code_out; job.pstride = policy_stride;
+  SmzArena dummy{};
+  k_bf16_chain<<<(n_rows + TM - 1) / TM, TM, im->smem_bytes, s>>>(dummy, im->chain_single[which], im->chain_single[which], job, 0);
+}

@@ -126,6 +126,74 @@ def test_fp32_network_step_matches_reference_inference(name):
     eng.close()
 
 
+# bf16 tensor-core mode: operands rounded to bf16 (8-bit mantissa) at every layer, fp32 accumulate.
+# Stated tolerances against the reference's fp32 outputs (measured worst case on these fixtures:
+# hidden 2.0e-3, policy 2.8e-4, value 3.5e-2 at |value| = 34): roughly 5x head-room.
+BF16_HIDDEN_ATOL = 1e-2
+BF16_POLICY_ATOL = 5e-3
+BF16_SCALAR_TOL = dict(atol=5e-3, rtol=5e-3)
+
+
+@pytest.mark.parametrize("name", golden_io.net_cases())
+def test_bf16_tcgen05_network_step_within_stated_tolerance(name):
+    z = golden_io.load_net_case(name)
+    eng = _net_engine(z, B=256, net="bf16")
+    h = dict(atol=BF16_HIDDEN_ATOL, rtol=0)
+    p = dict(atol=BF16_POLICY_ATOL, rtol=0)
+    np.testing.assert_allclose(eng.net_eval("repr", z["obs"])["hidden"].cpu().numpy(), z["repr_h"], **h)
+    o = eng.net_eval("pred", z["repr_h"])
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["pred_policy"], **p)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["pred_value"], **BF16_SCALAR_TOL)
+    np.testing.assert_allclose(eng.net_eval("adyn", z["repr_h"], z["actions"])["hidden"].cpu().numpy(), z["adyn_h"], **h)
+    o = eng.net_eval("apred", z["adyn_h"])
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["apred_policy"], **p)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["apred_value"], **BF16_SCALAR_TOL)
+    o = eng.net_eval("dyn", z["adyn_h"], z["actions"])
+    np.testing.assert_allclose(o["hidden"].cpu().numpy(), z["dyn_h"], **h)
+    np.testing.assert_allclose(o["reward"].cpu().numpy(), z["dyn_reward"], **BF16_SCALAR_TOL)
+    o = eng.net_eval("enc", z["obs"])
+    np.testing.assert_allclose(o["probs"].cpu().numpy(), z["enc_probs"], **p)
+    # a tile boundary: 300 rows = 2 full tiles + a ragged one, against the fp32 engine
+    g = np.random.default_rng(0)
+    obs = g.standard_normal((300, z["obs"].shape[1])).astype(np.float32)
+    e32 = _net_engine(z, B=300, net="fp32")
+    eng2 = _net_engine(z, B=300, net="bf16")
+    h32, h16 = e32.net_eval("repr", obs)["hidden"], eng2.net_eval("repr", obs)["hidden"]
+    np.testing.assert_allclose(h16.cpu().numpy(), h32.cpu().numpy(), **h)
+    acts = g.integers(0, int(z["dims"][1]), 300).astype(np.int32)
+    d32, d16 = e32.net_eval("dyn", h32, acts), eng2.net_eval("dyn", h32, acts)
+    np.testing.assert_allclose(d16["hidden"].cpu().numpy(), d32["hidden"].cpu().numpy(), **h)
+    np.testing.assert_allclose(d16["reward"].cpu().numpy(), d32["reward"].cpu().numpy(), **BF16_SCALAR_TOL)
+    for e in (eng, e32, eng2):
+        e.close()
+
+
+def test_bf16_search_is_self_consistent_with_the_oracle():
+    """Throughput mode end to end: device Philox + bf16 network.  The tree statistics must still be
+    the reference algorithm's, bit for bit, on the network outputs the engine actually produced."""
+    zn = golden_io.load_net_case("ckpt450")
+    B, N, seed = 300, 50, 99
+    eng = _net_engine(zn, B=B, N=N, net="bf16", rng="philox", seed=seed, record=True)
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(1))
+    eng.root(obs=obs, train=True)
+    eng.simulate(N)
+    eng.stats()
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    cfg = O.SearchConfig(discount=0.997, num_simulations=N, maxium_action_sample=2)
+    for b in (0, 127, 128, 255, 256, 299):
+        model = O.TapeModel(rec["root_policy"][b, :2], rec["sim_policy"][b], np.full(N, 2), rec["sim_value"][b],
+                            rec["sim_reward"][b])
+        tree = O.search(cfg, model, O.PhiloxUniforms(seed, b), train=True, dirichlet=rec["dirichlet"][b])
+        golden_io.assert_dump_equal(eng.export_tree(b), tree.dump(), f"bf16[{b}]")
+    # and the recorded outputs are what the fp32 oracle network gives on the same hidden states
+    net = NO.NetOracle(zn["weights"], *[int(v) for v in zn["dims"]])
+    h0 = eng.read_hidden(0).cpu().numpy()
+    np.testing.assert_allclose(h0, net.representation(obs.numpy()), atol=BF16_HIDDEN_ATOL)
+    pol, val = net.prediction(h0)
+    np.testing.assert_allclose(rec["root_policy"][:, :2], pol, atol=BF16_POLICY_ATOL)
+    eng.close()
+
+
 def _oracle_cfg(c):
     return O.SearchConfig(**{k: c[k] for k in ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha",
                                                 "root_exploration_fraction", "num_simulations",
