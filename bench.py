@@ -186,7 +186,7 @@ def main():
         a.record()
         step()
         b.record()
-        launches += 3 * N + 3
+        launches += 2 * N + 1 + 3     # select + N x (net, tree) + root net, dirichlet, root expand
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

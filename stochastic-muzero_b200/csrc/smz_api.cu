@@ -363,10 +363,12 @@ int smz_expand_backup(smz_engine* e, int32_t sim, const float* policy, const flo
 static void enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   const SmzArena& a = e->a;
   const int G = e->cfg.lanes_per_tree;
+  // select(first); then per simulation: network step, then [expand+backup(sim) fused with select(sim+1)]
+  smz_launch_select(a, G, e->n_trees, first, nullptr, nullptr, nullptr, s);
   for (int sim = first; sim < first + n_sims; ++sim) {
-    smz_launch_select(a, G, e->n_trees, sim, nullptr, nullptr, nullptr, s);
     enqueue_net(e, sim, s);
-    smz_launch_expand_backup(a, G, e->n_trees, sim, a.out_policy, a.W, a.out_value, a.out_reward, s);
+    if (sim + 1 < first + n_sims) smz_launch_backup_select(a, G, e->n_trees, sim, s);
+    else smz_launch_expand_backup(a, G, e->n_trees, sim, a.out_policy, a.W, a.out_value, a.out_reward, s);
   }
 }
 
@@ -396,7 +398,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     e->graph_trees = e->n_trees; e->graph_sims = n_sims; e->graph_first = first;
   }
   CU(cudaGraphLaunch(e->graph_exec, s));
-  e->launches += 3LL * n_sims;
+  e->launches += 2LL * n_sims + 1;
   e->sims_done += n_sims;
   return SMZ_OK;
 }

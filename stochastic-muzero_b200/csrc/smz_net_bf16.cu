@@ -26,6 +26,7 @@
 namespace {
 
 constexpr int TM = 128;                 // rows (leaves) per CTA == MMA M
+constexpr int NTHREADS = 512;           // 16 warps: 4 TMEM lane quarters x 4 column blocks
 constexpr int TN = 128;                 // MMA N (all layers padded to 128 output channels)
 constexpr int KMAX = 128;               // widest K
 constexpr int MAXL = 24;                // layers per chain: 2 * (L + 2), L <= 10
@@ -76,7 +77,7 @@ struct Smem {
   unsigned long long mbar;
   unsigned long long bbar;
   unsigned int tmem_base;
-  int index[TM];
+  float4 part[4][TM];       // per-row partial reductions of the head epilogues, one slot per column block
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -158,28 +159,43 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&p);
 }
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
-
 // store 8 consecutive K values of row r (already bf16-packed) into the canonical A operand
 __device__ __forceinline__ void a_store(unsigned char* a, int r, int kchunk, uint4 v) {
   *reinterpret_cast<uint4*>(a + kchunk * CHUNK_A + r * 16) = v;
 }
 
-// inverse_transform_with_support on S logits held in registers (muzero_model.py:575-591)
-__device__ __forceinline__ float support_scalar(const float* x, int S) {
-  float m = -INFINITY;
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ELU with the exponential on the MUFU pipe: exp(x) - 1 = 2^(x*log2e) - 1 (abs error ~1e-7, far below
+// the bf16 rounding the result gets next)
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2f(x * 1.4426950408889634f) - 1.f; }
+
+// partial softmax-expectation over this thread's 32 logits (columns col0..col0+31 of an S-wide head):
+// running max m, z = sum e^(x-m), y = sum (c - S/2) e^(x-m)
+struct SoftPart { float m, z, y; };
+__device__ __forceinline__ SoftPart soft_part(const float* x, int col0, int S) {
+  SoftPart p{-INFINITY, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 64; ++i) if (i < S) m = fmaxf(m, x[i]);
-  float z = 0.f, y = 0.f;
+  for (int i = 0; i < 32; ++i) if (col0 + i < S) p.m = fmaxf(p.m, x[i]);
   const int half = S / 2;
 #pragma unroll
-  for (int i = 0; i < 64; ++i)
-    if (i < S) {
-      const float e = __expf(x[i] - m);
-      z += e;
-      y += (float)(i - half) * e;
+  for (int i = 0; i < 32; ++i)
+    if (col0 + i < S) {
+      const float e = ex2f((x[i] - p.m) * 1.4426950408889634f);
+      p.z += e;
+      p.y += (float)(col0 + i - half) * e;
     }
-  y /= z;
+  return p;
+}
+// inverse_transform_with_support (muzero_model.py:575-591) from the two halves' partials
+__device__ __forceinline__ float support_scalar(SoftPart a, SoftPart b) {
+  const float m = fmaxf(a.m, b.m);
+  const float sa = a.m == -INFINITY ? 0.f : ex2f((a.m - m) * 1.4426950408889634f);
+  const float sb = b.m == -INFINITY ? 0.f : ex2f((b.m - m) * 1.4426950408889634f);
+  const float y = (a.y * sa + b.y * sb) / (a.z * sa + b.z * sb);
   const float inner = __fadd_rn(1.f, __fmul_rn(0.004f, __fadd_rn(__fadd_rn(fabsf(y), 1.f), 0.001f)));
   const float t = __fdiv_rn(__fsub_rn(__fsqrt_rn(inner), 1.f), 0.002f);
   const float mag = __fsub_rn(__fmul_rn(t, t), 1.f);
@@ -187,13 +203,17 @@ __device__ __forceinline__ float support_scalar(const float* x, int S) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// the fused chain kernel
+// the fused chain kernel: 512 threads = 16 warps; warp w owns TMEM lanes 32*(w%4).. (rows) and the
+// 32 accumulator columns 32*(w/4).. of every layer, so each SM sub-partition always has 4 warps to
+// interleave around the TMEM-load / MUFU latencies.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TM, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = (warp & 3) * 32 + lane;   // row of the tile == TMEM lane
+  const int cb = warp >> 2;               // column block: accumulator columns 32*cb .. 32*cb+31
 
   // ---- which rows does this CTA own? ------------------------------------------------------------
   int tile = blockIdx.x, branch = 0, count = job.n_rows;
@@ -207,7 +227,7 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     return;
   }
   const Chain& ch = branch ? chain1 : chain0;
-  const int row = tile * TM + tid;
+  const int row = tile * TM + r;
   const bool valid = row < count;
 
   // ---- barriers, TMEM, first weight tiles ---------------------------------------------------------
@@ -240,20 +260,19 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     if (ch.n_layers > 1) load_weights(1);
   }
 
-  // ---- stage the first A operand: one row per thread, bf16, canonical K-major layout ---------------
-  int index = -1;      // tree id (gather) or caller row
+  // ---- stage the first A operand: bf16, canonical K-major layout; thread (r, cb) fills its K-chunks ---
+  int index = -1;      // tree id (gather) or caller row: where this row's outputs go
   {
-    uint4 z4 = make_uint4(0, 0, 0, 0);
     if (job.input_kind == IN_OBS) {
       index = valid ? row : -1;
-      for (int kc = 0; kc < ch.kin / 8; ++kc) {
+      for (int kc = cb; kc < ch.kin / 8; kc += 4) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = kc * 8 + j;
           v[j] = (valid && c < job.obs) ? job.in[(size_t)row * job.obs + c] : 0.f;
         }
-        a_store(sm.a, tid, kc, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+        a_store(sm.a, r, kc, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
       }
     } else {
       const float* src = nullptr;
@@ -270,33 +289,34 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         }
       }
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        uint4 o = z4;
+      for (int q = 0; q < 2; ++q) {
+        const int kc = cb * 2 + q;
+        uint4 o = make_uint4(0, 0, 0, 0);
         if (valid) {
           const float4 lo = *reinterpret_cast<const float4*>(src + kc * 8);
           const float4 hi = *reinterpret_cast<const float4*>(src + kc * 8 + 4);
           o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
         }
-        a_store(sm.a, tid, kc, o);
+        a_store(sm.a, r, kc, o);
       }
-      for (int kc = 0; kc < ch.onehot_pad / 8; ++kc) {   // one-hot columns 64 + act
+      for (int kc = cb; kc < ch.onehot_pad / 8; kc += 4) {   // one-hot columns 64 + act
         unsigned w4[4] = {0, 0, 0, 0};
         if (valid && act >= kc * 8 && act < kc * 8 + 8) {
           const int j = act - kc * 8;
           w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
         }
-        a_store(sm.a, tid, 8 + kc, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+        a_store(sm.a, r, 8 + kc, make_uint4(w4[0], w4[1], w4[2], w4[3]));
       }
     }
   }
-  sm.index[tid] = index;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   mbar_wait(&sm.bbar, 0);
 
-  const unsigned lane_taddr = tmem + ((unsigned)(warp * 32) << 16);
+  const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(cb * 32);
   const int S = job.S;
+  const int c0 = cb * 32;
 
   // ---- the layer loop ---------------------------------------------------------------------------------
   for (int l = 0; l < ch.n_layers; ++l) {
@@ -313,104 +333,85 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     mbar_wait(&sm.mbar, l & 1);
     tc_fence_after();
     if (tid == 0 && l + 2 < ch.n_layers) load_weights(l + 2);   // ring slot l&1 is free again
-    const float* bias = sm.bias[l];
+    const float* bias = sm.bias[l] + c0;
+
+    float x[32];
+    tmem_ld32(taddr, x);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] += bias[j];
 
     if (kind == LK_HIDDEN) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        float v[32];
-        tmem_ld32(lane_taddr + c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + bias[c0 + j]);
+      for (int j = 0; j < 32; ++j) x[j] = elu_fast(x[j]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        a_store(sm.a, r, cb * 4 + q,
+                make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                           pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
+    } else {
+      // head layer: columns [0,64) = state or value logits, [64,128) = reward or policy logits.
+      // Row-wise reductions span two column blocks: partials meet in shared memory.
+      const bool state_seg = (kind == LK_STATE || kind == LK_STATE_REWARD) && cb < 2;
+      const bool soft_seg = (kind == LK_STATE_REWARD && cb >= 2) || (kind == LK_PRED && cb < 2);
+      SoftPart sp{-INFINITY, 0.f, 0.f};
+      if (state_seg) {
+        float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < S) { lo = fminf(lo, x[j]); hi = fmaxf(hi, x[j]); }
+        sm.part[cb][r] = make_float4(lo, hi, 0.f, 0.f);
+      } else if (soft_seg) {
+        sp = soft_part(x, c0 & 63, S);
+        sm.part[cb][r] = make_float4(sp.m, sp.z, sp.y, 0.f);
+      }
+      __syncthreads();
+      if (state_seg) {
+        // scale_to_bound_action (mlp:349-357): fp32 copy to HBM, bf16 copy = the next network's A operand
+        const float4 o = sm.part[cb ^ 1][r];
+        const float lo = fminf(sm.part[cb][r].x, o.x), hi = fmaxf(sm.part[cb][r].y, o.y);
+        float scale = hi - lo;
+        if (scale < 1e-5f) scale += 1e-5f;
+        const float inv = 1.f / scale;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = (c0 + j < S) ? (x[j] - lo) * inv : 0.f;
+        if (index >= 0 && job.hidden_dst) {
+          float4* dst = reinterpret_cast<float4*>(job.hidden_dst + (size_t)index * SMZ_SP + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          a_store(sm.a, tid, (c0 >> 3) + q,
-                  make_uint4(pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7])));
-      }
-    } else if (kind == LK_STATE || kind == LK_STATE_REWARD) {
-      // scale_to_bound_action over the S state logits of this row; fp32 copy to HBM, bf16 copy = next A
-      float x[64];
-      tmem_ld32(lane_taddr, x);
-      tmem_ld32(lane_taddr + 32, x + 32);
-      float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        x[i] += bias[i];
-        if (i < S) { lo = fminf(lo, x[i]); hi = fmaxf(hi, x[i]); }
-      }
-      float scale = hi - lo;
-      if (scale < 1e-5f) scale += 1e-5f;
-      const float inv = 1.f / scale;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) x[i] = i < S ? (x[i] - lo) * inv : 0.f;
-      if (index >= 0 && job.hidden_dst) {
-        float4* dst = reinterpret_cast<float4*>(job.hidden_dst + (size_t)index * SMZ_SP);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) dst[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        a_store(sm.a, tid, q, make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
-                                         pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
-      if (kind == LK_STATE_REWARD) {
-        tmem_ld32(lane_taddr + POL_OFF, x);
-        tmem_ld32(lane_taddr + POL_OFF + 32, x + 32);
-#pragma unroll
-        for (int i = 0; i < 64; ++i) x[i] += bias[POL_OFF + i];
-        const float r = support_scalar(x, S);
-        if (index >= 0 && job.reward_dst) job.reward_dst[index] = r;
-      }
-    } else if (kind == LK_PRED) {
-      float x[64];
-      tmem_ld32(lane_taddr, x);
-      tmem_ld32(lane_taddr + 32, x + 32);
-#pragma unroll
-      for (int i = 0; i < 64; ++i) x[i] += bias[i];
-      const float val = support_scalar(x, S);
-      if (index >= 0 && job.value_dst) job.value_dst[index] = val;
-      tmem_ld32(lane_taddr + POL_OFF, x);
-      const int n = ch.n_policy;
-      float m = -INFINITY, z = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        x[i] += bias[POL_OFF + i];
-        if (i < n) m = fmaxf(m, x[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        x[i] = i < n ? __expf(x[i] - m) : 0.f;
-        z += x[i];
-      }
-      if (index >= 0 && job.policy_dst) {
-        float* dst = job.policy_dst + (size_t)index * job.pstride;
-        const float inv = 1.f / z;
+          a_store(sm.a, r, cb * 4 + q,
+                  make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
+      } else if (soft_seg && (cb & 1) == 0) {
+        const float4 o = sm.part[cb + 1][r];
+        const float v = support_scalar(sp, SoftPart{o.x, o.y, o.z});
+        float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
+        if (index >= 0 && dst) dst[index] = v;
+      } else if ((kind == LK_PRED && cb == 2) || (kind == LK_CODE && cb == 0)) {
+        // policy softmax (muzero_model.py:837) / Encoder code distribution + argmax (mlp:209-250)
+        const int n = ch.n_policy;
+        float m = -INFINITY, z = 0.f;
+        int best = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < n) dst[i] = x[i] * inv;
-      }
-    } else {   // LK_CODE: Encoder (mlp:209-250) softmax over C code logits + argmax
-      float x[32];
-      tmem_ld32(lane_taddr, x);
-      const int n = ch.n_policy;
-      float m = -INFINITY, z = 0.f;
-      int best = 0;
+          if (i < n && x[i] > m) { m = x[i]; best = i; }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        x[i] += bias[i];
-        if (i < n && x[i] > m) { m = x[i]; best = i; }
-      }
+        for (int i = 0; i < 32; ++i) {
+          x[i] = i < n ? ex2f((x[i] - m) * 1.4426950408889634f) : 0.f;
+          z += x[i];
+        }
+        if (index >= 0) {
+          if (job.policy_dst) {
+            float* dst = job.policy_dst + (size_t)index * job.pstride;
+            const float inv = 1.f / z;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        x[i] = i < n ? __expf(x[i] - m) : 0.f;
-        z += x[i];
-      }
-      if (index >= 0) {
-        if (job.policy_dst)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < n) job.policy_dst[(size_t)index * job.pstride + i] = x[i] / z;
-        if (job.code_dst) job.code_dst[index] = best;
+            for (int i = 0; i < 32; ++i)
+              if (i < n) dst[i] = x[i] * inv;
+          }
+          if (kind == LK_CODE && job.code_dst) job.code_dst[index] = best;
+        }
       }
     }
     // make the new A operand visible to the tensor core (async proxy) and retire the TMEM reads
@@ -592,7 +593,7 @@ void smz_bf16_root(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, i
   Job job{};
   job.input_kind = IN_OBS; job.n_rows = n_trees; job.in = obs; job.obs = sh.obs; job.S = sh.S;
   job.hidden_dst = a.hidden; job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
-  k_bf16_chain<<<(n_trees + TM - 1) / TM, TM, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
+  k_bf16_chain<<<(n_trees + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
 }
 
 void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, cudaStream_t s) {
@@ -600,7 +601,7 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   job.input_kind = IN_GATHER; job.n_rows = n_trees; job.S = sh.S;
   job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * SMZ_SP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
-  k_bf16_chain<<<(n_trees + TM - 1) / TM + 1, TM, im->smem_bytes, s>>>(a, im->chain_after, im->chain_dyn, job, sim);
+  k_bf16_chain<<<(n_trees + TM - 1) / TM + 1, NTHREADS, im->smem_bytes, s>>>(a, im->chain_after, im->chain_dyn, job, sim);
 }
 
 void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_rows, const float* in, const int* idx,
@@ -612,5 +613,5 @@ void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_row
   job.hidden_dst = hidden_out; job.policy_dst = policy_out; job.value_dst = value_out; job.reward_dst = reward_out;
   job.code_dst = code_out; job.pstride = policy_stride;
   SmzArena dummy{};
-  k_bf16_chain<<<(n_rows + TM - 1) / TM, TM, im->smem_bytes, s>>>(dummy, im->chain_single[which], im->chain_single[which], job, 0);
+  k_bf16_chain<<<(n_rows + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(dummy, im->chain_single[which], im->chain_single[which], job, 0);
 }

