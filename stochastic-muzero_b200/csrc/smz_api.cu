@@ -140,7 +140,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.stat, B * M); ALLOC(a.link, B * M); ALLOC(a.root_prior, B * a.A); ALLOC(a.minmax, B);
   ALLOC(a.ucursor, B); ALLOC(a.root_to_play, B); ALLOC(a.path, B * a.path_stride); ALLOC(a.path_len, B);
   ALLOC(a.leaf_node, B); ALLOC(a.leaf_slot, B); ALLOC(a.leaf_action, B); ALLOC(a.leaf_branch, B);
-  ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 2 * B); ALLOC(a.error_flag, 1);
+  ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 2 * B); ALLOC(a.rows4, 2 * B); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
@@ -465,6 +465,11 @@ int smz_read_hidden(smz_engine* e, int32_t slot, float* out, void* stream) {
   if (!e->a.hidden) return fail(SMZ_E_STATE, "smz_read_hidden: engine has no internal network");
   if (slot < 0 || slot > e->a.N || e->n_trees < 1) return fail(SMZ_E_INVALID_ARG, "smz_read_hidden: bad slot");
   CU(cudaSetDevice(e->cfg.device));
+  if (e->bf16) {
+    smz_bf16_read_hidden(e->a, slot, e->n_trees, out, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return SMZ_OK;
+  }
   CU(cudaMemcpyAsync(out, e->a.hidden + (size_t)slot * e->a.B * SMZ_SP, (size_t)e->n_trees * SMZ_SP * sizeof(float),
                      cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SMZ_OK;

@@ -37,6 +37,7 @@ struct SmzArena {
   int* leaf_branch; // [B]
   int* branch_count; // [N+1][2] rows per branch of each simulation
   int* rows;        // [2][B] compacted tree ids per branch
+  int4* rows4;      // [2][B] same order: {tree, parent hidden slot, action, 0} — one load per gathered row
   int* error_flag;  // [1]
   unsigned long long* depth_sum;  // [1] sum of leaf depths (bench bookkeeping)
   // network I/O

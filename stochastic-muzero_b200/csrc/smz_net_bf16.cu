@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/smz.h"
@@ -60,13 +61,15 @@ struct Job {
   const float* in;          // IN_OBS: [n][obs]; IN_ROWS: [n][64]
   const int* idx;           // IN_ROWS: action / code per row (or null)
   int obs;                  // IN_OBS width
-  float* hidden_dst;        // [index][64] or null
+  float* hidden_dst;        // fp32 rows [index][64] (stand-alone evaluation) or null
+  __nv_bfloat16* hidden16_dst;  // bf16 rows [index][64] in the arena's hidden store, or null
   float* policy_dst;        // [index][pstride] or null
   float* value_dst;
   float* reward_dst;
   int* code_dst;
   int pstride;
   int S;
+  long long* timeline;      // debug: clock64 stamps of CTA 0 (null = off)
 };
 
 struct Smem {
@@ -94,6 +97,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 // bounded wait: a protocol error becomes a trap (CUDA error), never a hung GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned addr = s32(bar);
+#pragma unroll 1
   for (unsigned spin = 0; spin < (1u << 26); ++spin) {
     unsigned ok;
     asm volatile(
@@ -155,6 +159,18 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 columns, no wait (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld16_nowait(unsigned taddr, unsigned* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&p);
@@ -212,6 +228,8 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool stamp = job.timeline && blockIdx.x == 0 && tid == 0;
+  if (stamp) job.timeline[0] = clock64();
   const int r = (warp & 3) * 32 + lane;   // row of the tile == TMEM lane
   const int cb = warp >> 2;               // column block: accumulator columns 32*cb .. 32*cb+31
 
@@ -230,34 +248,30 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   const int row = tile * TM + r;
   const bool valid = row < count;
 
-  // ---- barriers, TMEM, first weight tiles ---------------------------------------------------------
-  if (tid == 0) {
-    mbar_init(&sm.wbar[0], 1);
-    mbar_init(&sm.wbar[1], 1);
-    mbar_init(&sm.mbar, 1);
-    mbar_init(&sm.bbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(TN)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const unsigned tmem = sm.tmem_base;
+  // ---- barriers + first weight tiles (one thread), TMEM allocation (warp 0): all of it overlaps the
+  //      dependent global loads of the gather below; one barrier publishes everything ----------------
   auto load_weights = [&](int l) {
     const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
     mbar_expect_tx(&sm.wbar[l & 1], bytes);
     bulk_g2s(sm.w[l & 1], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
   };
   if (tid == 0) {
+    mbar_init(&sm.wbar[0], 1);
+    mbar_init(&sm.wbar[1], 1);
+    mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.bbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const unsigned bbytes = (unsigned)ch.n_layers * TN * 4;
     mbar_expect_tx(&sm.bbar, bbytes);
     bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
     load_weights(0);
     if (ch.n_layers > 1) load_weights(1);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
   // ---- stage the first A operand: bf16, canonical K-major layout; thread (r, cb) fills its K-chunks ---
@@ -276,12 +290,14 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       }
     } else {
       const float* src = nullptr;
+      const __nv_bfloat16* src16 = nullptr;   // arena rows are already bf16: copied straight into the operand
       int act = -1;
       if (valid) {
         if (job.input_kind == IN_GATHER) {
-          index = a.rows[(size_t)branch * a.B + row];
-          src = a.hidden + ((size_t)a.leaf_slot[index] * a.B + index) * SMZ_SP;
-          act = a.leaf_action[index];
+          const int4 rec = a.rows4[(size_t)branch * a.B + row];     // {tree, parent slot, action, -}
+          index = rec.x;
+          src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + index) * SMZ_SP;
+          act = rec.z;
         } else {
           index = row;
           src = job.in + (size_t)row * SMZ_SP;
@@ -292,7 +308,9 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       for (int q = 0; q < 2; ++q) {
         const int kc = cb * 2 + q;
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (valid) {
+        if (valid && src16) {
+          o = *reinterpret_cast<const uint4*>(src16 + kc * 8);
+        } else if (valid) {
           const float4 lo = *reinterpret_cast<const float4*>(src + kc * 8);
           const float4 hi = *reinterpret_cast<const float4*>(src + kc * 8 + 4);
           o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
@@ -312,6 +330,8 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = sm.tmem_base;
   mbar_wait(&sm.bbar, 0);
 
   const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(cb * 32);
@@ -319,30 +339,50 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   const int c0 = cb * 32;
 
   // ---- the layer loop ---------------------------------------------------------------------------------
+  if (tid == 0) mbar_wait(&sm.wbar[0], 0);
   for (int l = 0; l < ch.n_layers; ++l) {
     const int K = ch.layer[l].K, kind = ch.layer[l].kind;
     if (tid == 0) {
-      mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
+      if (stamp) job.timeline[1 + l * 4 + 0] = clock64();
       tc_fence_after();
       const unsigned a_addr = s32(sm.a), w_addr = s32(sm.w[l & 1]);
       for (int k = 0; k < K / 16; ++k)
         umma(tmem, umma_desc(a_addr + k * 2 * CHUNK_A, CHUNK_A, 128), umma_desc(w_addr + k * 2 * CHUNK_W, CHUNK_W, 128),
              k > 0 ? 1u : 0u);
       umma_commit(&sm.mbar);
+      if (stamp) job.timeline[1 + l * 4 + 1] = clock64();
+      // the next layer's weights were requested two layers ago: absorb that wait while the MMAs run
+      if (l + 1 < ch.n_layers) mbar_wait(&sm.wbar[(l + 1) & 1], ((l + 1) >> 1) & 1);
     }
     mbar_wait(&sm.mbar, l & 1);
+    if (stamp) job.timeline[1 + l * 4 + 2] = clock64();
     tc_fence_after();
     if (tid == 0 && l + 2 < ch.n_layers) load_weights(l + 2);   // ring slot l&1 is free again
     const float* bias = sm.bias[l] + c0;
 
+    uint4 pend[4];                 // bf16 row pieces whose global store is deferred past the barrier
+    uint4* pend_dst = nullptr;
+    float4* pend32_dst = nullptr;
     float x[32];
-    tmem_ld32(taddr, x);
+    {
+      unsigned raw[32];
+      tmem_ld16_nowait(taddr, raw);
+      tmem_wait_ld();
+      tmem_ld16_nowait(taddr + 16, raw + 16);      // in flight while the first half is processed
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] += bias[j];
+      for (int j = 0; j < 16; ++j) {
+        x[j] = __uint_as_float(raw[j]) + bias[j];
+        if (kind == LK_HIDDEN) x[j] = elu_fast(x[j]);
+      }
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 16; j < 32; ++j) {
+        x[j] = __uint_as_float(raw[j]) + bias[j];
+        if (kind == LK_HIDDEN) x[j] = elu_fast(x[j]);
+      }
+    }
 
     if (kind == LK_HIDDEN) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = elu_fast(x[j]);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         a_store(sm.a, r, cb * 4 + q,
@@ -374,16 +414,14 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         const float inv = 1.f / scale;
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = (c0 + j < S) ? (x[j] - lo) * inv : 0.f;
-        if (index >= 0 && job.hidden_dst) {
-          float4* dst = reinterpret_cast<float4*>(job.hidden_dst + (size_t)index * SMZ_SP + c0);
+        if (index >= 0 && job.hidden_dst) pend32_dst = reinterpret_cast<float4*>(job.hidden_dst + (size_t)index * SMZ_SP + c0);
+        if (index >= 0 && job.hidden16_dst) pend_dst = reinterpret_cast<uint4*>(job.hidden16_dst + (size_t)index * SMZ_SP + c0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+        for (int q = 0; q < 4; ++q) {
+          pend[q] = make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                               pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+          a_store(sm.a, r, cb * 4 + q, pend[q]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          a_store(sm.a, r, cb * 4 + q,
-                  make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
-                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
       } else if (soft_seg && (cb & 1) == 0) {
         const float4 o = sm.part[cb + 1][r];
         const float v = support_scalar(sp, SoftPart{o.x, o.y, o.z});
@@ -414,12 +452,26 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         }
       }
     }
-    // make the new A operand visible to the tensor core (async proxy) and retire the TMEM reads
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
+    // make the new A operand visible to the tensor core (async proxy) and retire the TMEM reads.
+    // Global stores come AFTER the barrier: the proxy fence would otherwise wait for them to land.
+    if (l + 1 < ch.n_layers) {
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+    }
+    if (pend_dst) {           // the arena keeps hidden states in bf16: exactly what the next gather needs
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pend_dst[q] = pend[q];
+    }
+    if (pend32_dst) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pend32_dst[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+    }
+    if (stamp) job.timeline[1 + l * 4 + 3] = clock64();
   }
 
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TN) : "memory");
   }
@@ -438,6 +490,10 @@ __global__ void k_pack_bf16(__nv_bfloat16* __restrict__ dst, const float* __rest
   const int k = j < seg0 ? j : seg1_dst + (j - seg0);
   const int c = j < seg0 ? j : seg1_src + (j - seg0);
   dst[((size_t)(k >> 3) * TN + dst_n0 + n) * 8 + (k & 7)] = __float2bfloat16_rn(src[(size_t)n * in_stride + c]);
+}
+__global__ void k_bf16_to_f32(float* __restrict__ dst, const __nv_bfloat16* __restrict__ src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 __global__ void k_copy_f32(float* __restrict__ dst, const float* __restrict__ src, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,6 +519,7 @@ struct SmzBf16Image {
   unsigned char* pool;    // device: all images
   size_t pool_bytes;
   int smem_bytes;
+  long long* timeline;    // device debug buffer or null (SMZ_BF16_TIMELINE=1)
 };
 
 static int round16(int v) { return (v + 15) / 16 * 16; }
@@ -507,6 +564,10 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   }
   im->bias_pool = (float*)p;
   im->smem_bytes = (int)sizeof(Smem) + 1024;
+  if (getenv("SMZ_BF16_TIMELINE")) {
+    cudaMalloc(&im->timeline, (1 + 4 * MAXL) * sizeof(long long));
+    cudaMemset(im->timeline, 0, (1 + 4 * MAXL) * sizeof(long long));
+  }
   cudaFuncSetAttribute((const void*)k_bf16_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
   *out = im;
   return SMZ_OK;
@@ -514,6 +575,17 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
 
 void smz_bf16_destroy(SmzBf16Image* im) {
   if (!im) return;
+  if (im->timeline) {
+    long long t[1 + 4 * MAXL];
+    if (cudaMemcpy(t, im->timeline, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "smz bf16 timeline (cycles, CTA 0 of the last simulation step):\n");
+      for (int l = 0; l < MAXL && t[1 + l * 4 + 3]; ++l)
+        fprintf(stderr, "  layer %2d: start +%6lld | mma issue %5lld | issue->done (all threads) %5lld | epilogue+sync %5lld\n", l,
+                t[1 + l * 4] - t[0], t[1 + l * 4 + 1] - t[1 + l * 4], t[1 + l * 4 + 2] - t[1 + l * 4 + 1],
+                t[1 + l * 4 + 3] - t[1 + l * 4 + 2]);
+    }
+    cudaFree(im->timeline);
+  }
   cudaFree(im->pool);
   delete im;
 }
@@ -589,18 +661,26 @@ int smz_bf16_pack(SmzBf16Image* im, const SmzNetShape& sh, const float* blob, cu
   return SMZ_OK;
 }
 
+void smz_bf16_read_hidden(const SmzArena& a, int slot, int n_trees, float* out, cudaStream_t s) {
+  const size_t n = (size_t)n_trees * SMZ_SP;
+  k_bf16_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      out, reinterpret_cast<const __nv_bfloat16*>(a.hidden) + (size_t)slot * a.B * SMZ_SP, n);
+}
+
 void smz_bf16_root(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, const float* obs, cudaStream_t s) {
   Job job{};
   job.input_kind = IN_OBS; job.n_rows = n_trees; job.in = obs; job.obs = sh.obs; job.S = sh.S;
-  job.hidden_dst = a.hidden; job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
+  job.hidden16_dst = reinterpret_cast<__nv_bfloat16*>(a.hidden);
+  job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
   k_bf16_chain<<<(n_trees + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
 }
 
 void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, cudaStream_t s) {
   Job job{};
   job.input_kind = IN_GATHER; job.n_rows = n_trees; job.S = sh.S;
-  job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * SMZ_SP;
+  job.hidden16_dst = reinterpret_cast<__nv_bfloat16*>(a.hidden) + (size_t)(sim + 1) * a.B * SMZ_SP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
+  job.timeline = im->timeline;
   k_bf16_chain<<<(n_trees + TM - 1) / TM + 1, NTHREADS, im->smem_bytes, s>>>(a, im->chain_after, im->chain_dyn, job, sim);
 }
 

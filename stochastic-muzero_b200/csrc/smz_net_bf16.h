@@ -17,3 +17,5 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
 void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_rows, const float* in, const int* idx,
                    float* hidden_out, float* policy_out, float* value_out, float* reward_out, int* code_out,
                    int policy_stride, cudaStream_t s);
+// bf16 mode keeps the arena's hidden-state store in bf16 ([slot][B][64]); this widens one slot to fp32 rows
+void smz_bf16_read_hidden(const SmzArena& a, int slot, int n_trees, float* out, cudaStream_t s);

@@ -260,6 +260,7 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     if (o_branch) o_branch[tree] = branch;
     const int r = atomicAdd(&a.branch_count[sim * 2 + branch], 1);
     a.rows[(size_t)branch * a.B + r] = tree;
+    a.rows4[(size_t)branch * a.B + r] = make_int4(tree, slot, child_key, 0);
     atomicAdd(a.depth_sum, (unsigned long long)(depth + 1));
   }
 }
