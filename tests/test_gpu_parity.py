@@ -336,3 +336,51 @@ def test_dropin_run_with_callback_model_matches_oracle_statistics():
     deep = [c for c in root.children.values() if c.expanded()][0]
     assert all(g.is_chance for g in deep.children.values())
     assert deep.hidden_state.shape == (1, 11)
+
+
+def test_shard_invariance_philox_keyed_by_global_tree_id():
+    """B trees on one engine == the same trees split over two engines with tree_id_offset (what the
+    multi-GPU sharding does): identical per-tree results, bit for bit."""
+    zn = golden_io.load_net_case("mlp450_seed0")
+    B, N, seed = 256, 50, 4242
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(3))
+    whole = _net_engine(zn, B=B, N=N, rng="philox", seed=seed)
+    whole.root(obs=obs, train=True); whole.simulate(N)
+    full = {k: v.cpu().numpy() for k, v in whole.read_roots().items()}
+    parts = []
+    for lo, hi in ((0, 100), (100, 256)):
+        e = _net_engine(zn, B=hi - lo, N=N, rng="philox", seed=seed, tree_id_offset=lo)
+        e.root(obs=obs[lo:hi], train=True); e.simulate(N)
+        parts.append({k: v.cpu().numpy() for k, v in e.read_roots().items()})
+        e.close()
+    for k in full:
+        assert np.array_equal(full[k], np.concatenate([p[k] for p in parts])), k
+    whole.close()
+
+
+def test_wide_chance_codebook_full_search_config3_shape():
+    """BASELINE config 3 shape (4 actions, 32 chance codes, K=32, N=100) with the internal fp32
+    network on synthetic 4x4 boards: engine record replayed by the oracle."""
+    from stochastic_muzero_b200 import ModelShape, SearchEngine
+    from stochastic_muzero_b200.weights import random_blob
+    shape = ModelShape(obs_dim=16, action_dim=4, chance_dim=32, state_dim=61, hidden_dim=126, num_hidden_layers=4)
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=100, maxium_action_sample=32,
+                  number_of_player=1, custom_loop=None)
+    B, seed = 64, 31
+    g = np.random.default_rng(0)
+    obs = (g.integers(0, 12, (B, 16)) / 16.0).astype(np.float32)
+    for net in ("fp32", "bf16"):
+        eng = SearchEngine(search, 4, 32, max_trees=B, model_shape=shape, net=net, rng="philox", seed=seed, record=True)
+        eng.set_weights(random_blob(shape, seed=3))
+        eng.root(obs=obs, train=True); eng.simulate(100)
+        eng.stats()
+        rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+        cfg = O.SearchConfig(**search)
+        for b in (0, 31, 63):
+            width = np.where(rec["sim_branch"][b] == 1, 4, 32)
+            model = O.TapeModel(rec["root_policy"][b, :4], rec["sim_policy"][b], width, rec["sim_value"][b], rec["sim_reward"][b])
+            tree = O.search(cfg, model, O.PhiloxUniforms(seed, b), train=True, dirichlet=rec["dirichlet"][b])
+            golden_io.assert_dump_equal(eng.export_tree(b), tree.dump(), f"cfg3-{net}[{b}]")
+        assert (eng.read_roots()["visits"].sum(1) == 100).all()
+        eng.close()
