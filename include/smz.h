@@ -115,9 +115,10 @@ int smz_destroy(smz_engine* e);
 int smz_get_dims(const smz_engine* e, smz_dims* out);
 const char* smz_last_error(void);
 
-/* pb_c(n) = log((n + base + 1)/base) + init for n = 0..N (monte_carlo_tree_search.py:236).  The
- * engine fills the table with the C library's log(); a host that needs bit-equality with numpy's
- * np.log on the same machine passes its own table (n_entries must be N + 2). */
+/* Exploration prefactor table t[n] = sqrt(n) * (log((n + base + 1)/base) + init) for parent visit
+ * counts n = 0..N+1 — the left-associated head of `np.sqrt(N) * pb_c * prior` (monte_carlo_tree_search.py:
+ * 236-237).  The engine fills it with the C library's sqrt()/log(); a host that needs bit-equality with
+ * numpy on the same machine passes its own table (n_entries must be N + 2). */
 int smz_set_pbc_table(smz_engine* e, const double* table_host, int32_t n_entries);
 
 /* Player_cycle (monte_carlo_tree_search.py:38-72) flattened per depth.  For each of n_phases

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -50,6 +51,7 @@ struct smz_engine {
   cudaGraphExec_t graph_exec;
   int graph_trees, graph_sims, graph_first;
   cudaStream_t capture_stream;
+  int use_pdl;
 };
 
 const char* smz_last_error(void) { return g_err; }
@@ -69,7 +71,7 @@ static int fill_default_tables(smz_engine* e) {
   const int n = c.num_simulations + 2;
   std::vector<double> pbc(n);
   for (int i = 0; i < n; ++i)
-    pbc[i] = log(((double)i + (double)c.pb_c_base + 1.0) / (double)c.pb_c_base) + c.pb_c_init;
+    pbc[i] = sqrt((double)i) * (log(((double)i + (double)c.pb_c_base + 1.0) / (double)c.pb_c_base) + c.pb_c_init);
   CU(cudaMemcpy(e->pbc_dev, pbc.data(), n * sizeof(double), cudaMemcpyHostToDevice));
   std::vector<signed char> sign(n, 1);
   CU(cudaMemcpy(e->sign_dev, sign.data(), n, cudaMemcpyHostToDevice));
@@ -100,7 +102,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   int need = pow2ceil(c.action_dim > c.chance_dim ? c.action_dim : c.chance_dim);
   if (need < 2) need = 2;
   int lanes = c.lanes_per_tree;
-  if (lanes == 0) lanes = need < 8 ? 8 : need;
+  if (lanes == 0) lanes = need < 4 ? 4 : need;
   if ((lanes & (lanes - 1)) || lanes < need || lanes > 32)
     return fail(SMZ_E_INVALID_ARG, "smz_create: lanes_per_tree must be a power of two in [%d, 32]", need);
 
@@ -111,6 +113,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   memset(&e->a, 0, sizeof(e->a));
   e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr;
   e->n_trees = 0; e->sims_done = 0; e->have_weights = 0; e->launches = 0;
+  e->use_pdl = getenv("SMZ_NO_PDL") ? 0 : 1;
   e->graph_exec = nullptr; e->graph_trees = e->graph_sims = e->graph_first = -1; e->capture_stream = nullptr;
 
   SmzArena& a = e->a;
@@ -328,8 +331,8 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32
   return SMZ_OK;
 }
 
-static void enqueue_net(smz_engine* e, int sim, cudaStream_t s) {
-  if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, s);
+static void enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false) {
+  if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, s);
   else smz_net_f32_sim(e->a, e->shape, e->img32, e->n_trees, sim, s);
 }
 
@@ -364,10 +367,13 @@ static void enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   const SmzArena& a = e->a;
   const int G = e->cfg.lanes_per_tree;
   // select(first); then per simulation: network step, then [expand+backup(sim) fused with select(sim+1)]
+  // With the tensor-core network both hot kernels are chained by programmatic dependent launch: the
+  // next kernel's CTAs become resident and run their prologue while the previous one drains.
+  const bool pdl = e->bf16 != nullptr && e->use_pdl;
   smz_launch_select(a, G, e->n_trees, first, nullptr, nullptr, nullptr, s);
   for (int sim = first; sim < first + n_sims; ++sim) {
-    enqueue_net(e, sim, s);
-    if (sim + 1 < first + n_sims) smz_launch_backup_select(a, G, e->n_trees, sim, s);
+    enqueue_net(e, sim, s, pdl);
+    if (sim + 1 < first + n_sims) smz_launch_backup_select(a, G, e->n_trees, sim, pdl, s);
     else smz_launch_expand_backup(a, G, e->n_trees, sim, a.out_policy, a.W, a.out_value, a.out_reward, s);
   }
 }
@@ -391,10 +397,18 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     CU(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
     enqueue_sims(e, first, n_sims, e->capture_stream);
     cudaError_t ce = cudaStreamEndCapture(e->capture_stream, &graph);
-    if (ce != cudaSuccess) return fail(SMZ_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail(SMZ_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+    if (ce == cudaSuccess) {
+      ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+    }
+    if (ce != cudaSuccess && e->use_pdl && e->bf16) {
+      // programmatic edges not capturable on this driver: fall back to plain stream order, once
+      cudaGetLastError();
+      e->graph_exec = nullptr;
+      e->use_pdl = 0;
+      return smz_simulate(e, n_sims, stream);
+    }
+    if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail(SMZ_E_CUDA, "graph capture/instantiate failed: %s", cudaGetErrorString(ce)); }
     e->graph_trees = e->n_trees; e->graph_sims = n_sims; e->graph_first = first;
   }
   CU(cudaGraphLaunch(e->graph_exec, s));

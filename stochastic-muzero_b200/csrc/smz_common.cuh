@@ -58,7 +58,7 @@ struct SmzArena {
   int tape_stride;
   const unsigned long long* seed_state;  // device [2]: {Philox key, global id of local tree 0}
   // constants
-  const double* pbc;         // [N+2]
+  const double* pbc;         // [N+2]: sqrt(n) * (log((n + base + 1)/base) + init)
   const signed char* sign;   // [n_phases][N+2]
   float discount;
   float one_minus_frac_f32;  // f32(1 - frac), the weak-scalar cast the reference performs
@@ -67,6 +67,23 @@ struct SmzArena {
 };
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): `smz_pdl_wait` blocks until the preceding kernel of the stream has
+// completed and its writes are visible (no-op when the launch carries no programmatic dependency);
+// `smz_pdl_launch_dependents` lets the next kernel's CTAs become resident and run their prologue.
+__device__ __forceinline__ void smz_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void smz_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t smz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10, counter = (index>>1, stream, tree_lo, tree_hi), key = (seed_lo, seed_hi)
 // (restated on the CPU in oracle/mcts_oracle.py::philox_uniform and oracle/c/smz_oracle.c)

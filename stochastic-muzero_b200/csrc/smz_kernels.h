@@ -13,7 +13,7 @@ void smz_launch_select(const SmzArena& a, int lanes, int n_trees, int sim, int* 
 void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim, const float* policy, int pstride,
                               const float* value, const float* reward, cudaStream_t s);
 // expand+backup of `sim` fused with the descent of `sim + 1` (internal-network loop)
-void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, cudaStream_t s);
+void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s);
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,
                            cudaStream_t s);
 void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s);

@@ -192,25 +192,25 @@ __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2f(x
 // partial softmax-expectation over this thread's 32 logits (columns col0..col0+31 of an S-wide head):
 // running max m, z = sum e^(x-m), y = sum (c - S/2) e^(x-m)
 struct SoftPart { float m, z, y; };
+// Padded columns (>= S) need no predicate: their bias is -1e30 in the weight image, so e == 0.
 __device__ __forceinline__ SoftPart soft_part(const float* x, int col0, int S) {
-  SoftPart p{-INFINITY, 0.f, 0.f};
+  SoftPart p{-1e30f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 32; ++i) if (col0 + i < S) p.m = fmaxf(p.m, x[i]);
-  const int half = S / 2;
+  for (int i = 0; i < 32; ++i) p.m = fmaxf(p.m, x[i]);
+  const float base = (float)(col0 - S / 2);
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (col0 + i < S) {
-      const float e = ex2f((x[i] - p.m) * 1.4426950408889634f);
-      p.z += e;
-      p.y += (float)(col0 + i - half) * e;
-    }
+  for (int i = 0; i < 32; ++i) {
+    const float e = ex2f((x[i] - p.m) * 1.4426950408889634f);
+    p.z += e;
+    p.y = fmaf(base + (float)i, e, p.y);
+  }
   return p;
 }
 // inverse_transform_with_support (muzero_model.py:575-591) from the two halves' partials
 __device__ __forceinline__ float support_scalar(SoftPart a, SoftPart b) {
   const float m = fmaxf(a.m, b.m);
-  const float sa = a.m == -INFINITY ? 0.f : ex2f((a.m - m) * 1.4426950408889634f);
-  const float sb = b.m == -INFINITY ? 0.f : ex2f((b.m - m) * 1.4426950408889634f);
+  const float sa = ex2f((a.m - m) * 1.4426950408889634f);     // a fully padded half has z == y == 0
+  const float sb = ex2f((b.m - m) * 1.4426950408889634f);
   const float y = (a.y * sa + b.y * sb) / (a.z * sa + b.z * sb);
   const float inner = __fadd_rn(1.f, __fmul_rn(0.004f, __fadd_rn(__fadd_rn(fabsf(y), 1.f), 0.001f)));
   const float t = __fdiv_rn(__fsub_rn(__fsqrt_rn(inner), 1.f), 0.002f);
@@ -233,20 +233,16 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   const int r = (warp & 3) * 32 + lane;   // row of the tile == TMEM lane
   const int cb = warp >> 2;               // column block: accumulator columns 32*cb .. 32*cb+31
 
-  // ---- which rows does this CTA own? ------------------------------------------------------------
-  int tile = blockIdx.x, branch = 0, count = job.n_rows;
+  // ---- which rows does this CTA own?  Gather launches use a static split: CTAs [0, T) serve the
+  //      afterstate rows, [T, 2T) the dynamics rows (T = tiles of the whole batch), so the branch —
+  //      and with it the weight chain — is known before the previous kernel has finished. -------------
+  int tile = blockIdx.x, branch = 0;
   if (job.input_kind == IN_GATHER) {
-    const int n0 = a.branch_count[sim * 2 + 0], n1 = a.branch_count[sim * 2 + 1];
-    const int t0 = (n0 + TM - 1) / TM, t1 = (n1 + TM - 1) / TM;
-    if (tile < t0) { branch = 0; count = n0; }
-    else if (tile < t0 + t1) { branch = 1; count = n1; tile -= t0; }
-    else return;
-  } else if (tile * TM >= count) {
-    return;
+    const int T = (job.n_rows + TM - 1) / TM;
+    branch = tile >= T;
+    tile -= branch * T;
   }
   const Chain& ch = branch ? chain1 : chain0;
-  const int row = tile * TM + r;
-  const bool valid = row < count;
 
   // ---- barriers + first weight tiles (one thread), TMEM allocation (warp 0): all of it overlaps the
   //      dependent global loads of the gather below; one barrier publishes everything ----------------
@@ -272,6 +268,27 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(TN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---- everything above is independent of the previous kernel; from here on we read its results ---
+  smz_pdl_launch_dependents();
+  smz_pdl_wait();
+  int count = job.n_rows;
+  if (job.input_kind == IN_GATHER) count = a.branch_count[sim * 2 + branch];
+  const int row = tile * TM + r;
+  const bool valid = row < count;
+  if (tile * TM >= count) {        // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
+    if (tid == 0) {
+      mbar_wait(&sm.bbar, 0);
+      mbar_wait(&sm.wbar[0], 0);
+      if (ch.n_layers > 1) mbar_wait(&sm.wbar[1], 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(TN) : "memory");
+    return;
   }
 
   // ---- stage the first A operand: bf16, canonical K-major layout; thread (r, cb) fills its K-chunks ---
@@ -382,6 +399,8 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       }
     }
 
+    long long* hs = (stamp && kind != LK_HIDDEN) ? job.timeline + 1 + 4 * MAXL + (kind == LK_PRED ? 8 : 0) : nullptr;
+    if (hs) hs[0] = clock64();
     if (kind == LK_HIDDEN) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -398,13 +417,15 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c0 + j < S) { lo = fminf(lo, x[j]); hi = fmaxf(hi, x[j]); }
+          { lo = fminf(lo, x[j]); hi = fmaxf(hi, x[j]); }   // padded columns replicate column 0 (weight image)
         sm.part[cb][r] = make_float4(lo, hi, 0.f, 0.f);
       } else if (soft_seg) {
         sp = soft_part(x, c0 & 63, S);
         sm.part[cb][r] = make_float4(sp.m, sp.z, sp.y, 0.f);
       }
+      if (hs) hs[1] = clock64();
       __syncthreads();
+      if (hs) hs[2] = clock64();
       if (state_seg) {
         // scale_to_bound_action (mlp:349-357): fp32 copy to HBM, bf16 copy = the next network's A operand
         const float4 o = sm.part[cb ^ 1][r];
@@ -413,7 +434,7 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         if (scale < 1e-5f) scale += 1e-5f;
         const float inv = 1.f / scale;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = (c0 + j < S) ? (x[j] - lo) * inv : 0.f;
+        for (int j = 0; j < 32; ++j) x[j] = (x[j] - lo) * inv;   // padded columns: finite copies, zero weights next
         if (index >= 0 && job.hidden_dst) pend32_dst = reinterpret_cast<float4*>(job.hidden_dst + (size_t)index * SMZ_SP + c0);
         if (index >= 0 && job.hidden16_dst) pend_dst = reinterpret_cast<uint4*>(job.hidden16_dst + (size_t)index * SMZ_SP + c0);
 #pragma unroll
@@ -430,14 +451,14 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       } else if ((kind == LK_PRED && cb == 2) || (kind == LK_CODE && cb == 0)) {
         // policy softmax (muzero_model.py:837) / Encoder code distribution + argmax (mlp:209-250)
         const int n = ch.n_policy;
-        float m = -INFINITY, z = 0.f;
+        float m = -1e30f, z = 0.f;
         int best = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < n && x[i] > m) { m = x[i]; best = i; }
+          if (x[i] > m) { m = x[i]; best = i; }             // padded logits sit at -1e30 (bias)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          x[i] = i < n ? ex2f((x[i] - m) * 1.4426950408889634f) : 0.f;
+          x[i] = ex2f((x[i] - m) * 1.4426950408889634f);
           z += x[i];
         }
         if (index >= 0) {
@@ -452,6 +473,7 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         }
       }
     }
+    if (hs) hs[3] = clock64();
     // make the new A operand visible to the tensor core (async proxy) and retire the TMEM reads.
     // Global stores come AFTER the barrier: the proxy fence would otherwise wait for them to land.
     if (l + 1 < ch.n_layers) {
@@ -459,6 +481,7 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       tc_fence_before();
       __syncthreads();
     }
+    if (hs) hs[4] = clock64();
     if (pend_dst) {           // the arena keeps hidden states in bf16: exactly what the next gather needs
 #pragma unroll
       for (int q = 0; q < 4; ++q) pend_dst[q] = pend[q];
@@ -494,6 +517,20 @@ __global__ void k_pack_bf16(__nv_bfloat16* __restrict__ dst, const float* __rest
 __global__ void k_bf16_to_f32(float* __restrict__ dst, const __nv_bfloat16* __restrict__ src, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+// state head: columns [S, 64) replicate column 0 so that they never move the row min / max
+__global__ void k_replicate_col0(__nv_bfloat16* __restrict__ w, float* __restrict__ b, int S, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over (64 - S) * K
+  const int npad = 64 - S;
+  if (i >= npad * K) return;
+  const int n = S + i / K, k = i % K;
+  w[((size_t)(k >> 3) * TN + n) * 8 + (k & 7)] = w[((size_t)(k >> 3) * TN + 0) * 8 + (k & 7)];
+  if (k == 0) b[n] = b[0];
+}
+// softmax heads: padded logits get bias -1e30 (weights stay zero) => probability exactly 0
+__global__ void k_fill_f32(float* __restrict__ dst, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
 }
 __global__ void k_copy_f32(float* __restrict__ dst, const float* __restrict__ src, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,8 +602,8 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   im->bias_pool = (float*)p;
   im->smem_bytes = (int)sizeof(Smem) + 1024;
   if (getenv("SMZ_BF16_TIMELINE")) {
-    cudaMalloc(&im->timeline, (1 + 4 * MAXL) * sizeof(long long));
-    cudaMemset(im->timeline, 0, (1 + 4 * MAXL) * sizeof(long long));
+    cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
+    cudaMemset(im->timeline, 0, (1 + 4 * MAXL + 16) * sizeof(long long));
   }
   cudaFuncSetAttribute((const void*)k_bf16_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
   *out = im;
@@ -576,13 +613,17 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
 void smz_bf16_destroy(SmzBf16Image* im) {
   if (!im) return;
   if (im->timeline) {
-    long long t[1 + 4 * MAXL];
+    long long t[1 + 4 * MAXL + 16];
     if (cudaMemcpy(t, im->timeline, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "smz bf16 timeline (cycles, CTA 0 of the last simulation step):\n");
       for (int l = 0; l < MAXL && t[1 + l * 4 + 3]; ++l)
         fprintf(stderr, "  layer %2d: start +%6lld | mma issue %5lld | issue->done (all threads) %5lld | epilogue+sync %5lld\n", l,
                 t[1 + l * 4] - t[0], t[1 + l * 4 + 1] - t[1 + l * 4], t[1 + l * 4 + 2] - t[1 + l * 4 + 1],
                 t[1 + l * 4 + 3] - t[1 + l * 4 + 2]);
+      const long long* h = t + 1 + 4 * MAXL;
+      for (int k = 0; k < 2; ++k, h += 8)
+        fprintf(stderr, "  %s head (thread 0): load+bias -> partials %lld | barrier %lld | finish %lld | fence+barrier %lld\n",
+                k ? "pred " : "state", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
     }
     cudaFree(im->timeline);
   }
@@ -637,16 +678,22 @@ int smz_bf16_pack(SmzBf16Image* im, const SmzNetShape& sh, const float* blob, cu
     pack(n.in_w, H, in_dim[t], live, 64, S, oh ? OH : 0, 0);
     vec(n.in_b, H);
     if (sh.L > 0) { pack(n.mid_w, H, H, H, 0, 0, 0, 0); vec(n.mid_b, H); }
+    auto neg = [&](float* dst, int cnt) { if (cnt > 0) k_fill_f32<<<1, 128, 0, s>>>(dst, -1e30f, cnt); };
+    auto rep = [&](NetImg& m) { const int c = (64 - S) * KMAX; if (c > 0) k_replicate_col0<<<(c + 255) / 256, 256, 0, s>>>(m.head_w, m.head_b, S, KMAX); };
     switch (t) {
-      case 0: pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  // repr: state
-      case 1: pack(n.head_w, A, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, A);                          // pred: policy,
+      case 0: pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); rep(n); break;                          // repr: state
+      case 1: neg(n.head_b + S, 64 - S); neg(n.head_b + POL_OFF + A, 64 - A);
+              pack(n.head_w, A, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, A);                          // pred: policy,
               pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  //       value
-      case 2: pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  // adyn: state
-      case 3: pack(n.head_w, C, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, C);
+      case 2: pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); rep(n); break;                          // adyn: state
+      case 3: neg(n.head_b + S, 64 - S); neg(n.head_b + POL_OFF + C, 64 - C);
+              pack(n.head_w, C, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, C);
               pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;
-      case 4: pack(n.head_w, S, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, S);                          // dyn: reward,
-              pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); break;                                  //      state
-      case 5: pack(n.head_w, C, H, H, 0, 0, 0, 0); vec(n.head_b, C); break;                                  // enc: code
+      case 4: neg(n.head_b + POL_OFF + S, 64 - S);
+              pack(n.head_w, S, H, H, 0, 0, 0, POL_OFF); vec(n.head_b + POL_OFF, S);                          // dyn: reward,
+              pack(n.head_w, S, H, H, 0, 0, 0, 0); vec(n.head_b, S); rep(n); break;                          //      state
+      case 5: neg(n.head_b + C, 128 - C);
+              pack(n.head_w, C, H, H, 0, 0, 0, 0); vec(n.head_b, C); break;                                  // enc: code
     }
   }
   float* bp = im->bias_pool;
@@ -675,13 +722,15 @@ void smz_bf16_root(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, i
   k_bf16_chain<<<(n_trees + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
 }
 
-void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, cudaStream_t s) {
+void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, bool pdl,
+                  cudaStream_t s) {
   Job job{};
   job.input_kind = IN_GATHER; job.n_rows = n_trees; job.S = sh.S;
   job.hidden16_dst = reinterpret_cast<__nv_bfloat16*>(a.hidden) + (size_t)(sim + 1) * a.B * SMZ_SP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   job.timeline = im->timeline;
-  k_bf16_chain<<<(n_trees + TM - 1) / TM + 1, NTHREADS, im->smem_bytes, s>>>(a, im->chain_after, im->chain_dyn, job, sim);
+  smz_launch(k_bf16_chain, dim3(2 * ((n_trees + TM - 1) / TM)), dim3(NTHREADS), (size_t)im->smem_bytes, s, pdl, a,
+             im->chain_after, im->chain_dyn, job, sim);
 }
 
 void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_rows, const float* in, const int* idx,

@@ -206,8 +206,8 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       if (act && !chance) {
         const double prior = (depth == 0) ? a.root_prior[(size_t)tree * a.A + g.gl] : (double)__int_as_float(st.w);
         const double u = smz_uniform(a, tree, cursor + g.gl);
-        const double pb_c = a.pbc[parent_visit];
-        const double ps = __ddiv_rn(__dmul_rn(__dmul_rn(sqrt((double)parent_visit), pb_c), prior), (double)(st.x + 1));
+        // a.pbc[n] = sqrt(n) * pb_c(n), the left-associated head of mcts.py:237, tabulated by the host
+        const double ps = __ddiv_rn(__dmul_rn(a.pbc[parent_visit], prior), (double)(st.x + 1));
         double vs = 0.0;
         if (st.x > 0) {
           const float val = __fdiv_rn(__int_as_float(st.y), (float)st.x);
@@ -373,6 +373,8 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
 // re-read from L1/L2.
 template <int G>
 __global__ void k_backup_select(SmzArena a, int n_trees, int sim) {
+  smz_pdl_wait();                 // the network step of `sim` must have landed
+  smz_pdl_launch_dependents();    // the next network step may set itself up (barriers, TMEM, weights)
   Group<G> g;
   int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool alive = tree < n_trees;
@@ -461,8 +463,9 @@ void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim
                             a, n_trees, sim, policy, pstride, value, reward)));
 }
 
-void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, cudaStream_t s) {
-  SMZ_DISPATCH_G(lanes, (k_backup_select<G><<<grid_for<G>(n_trees, kThreads), kThreads, 0, s>>>(a, n_trees, sim)));
+void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s) {
+  SMZ_DISPATCH_G(lanes, (smz_launch(k_backup_select<G>, dim3(grid_for<G>(n_trees, kThreads)), dim3(kThreads), 0, s, pdl,
+                                    a, n_trees, sim)));
 }
 
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,

@@ -98,9 +98,10 @@ class SearchEngine:
         self.max_trees = int(max_trees)
         self.n_trees = 0
         self._keep = {}           # tensors the engine holds raw pointers to
-        # pb_c(n) with numpy's log, exactly as monte_carlo_tree_search.py:236 evaluates it on this host
+        # sqrt(n) * pb_c(n) with numpy's sqrt/log, exactly as monte_carlo_tree_search.py:236-237 evaluates
+        # `np.sqrt(parent.visit_count) * pb_c` on this host (the product is then multiplied by the prior)
         base, init = int(search["pb_c_base"]), float(search["pb_c_init"])
-        pbc = np.array([np.log((n + base + 1) / base) + init for n in range(self.N + 2)], np.float64)
+        pbc = np.array([np.sqrt(n) * (np.log((n + base + 1) / base) + init) for n in range(self.N + 2)], np.float64)
         self._check(self.lib.smz_set_pbc_table(self._h, pbc.ctypes.data_as(C.POINTER(C.c_double)), len(pbc)))
         sign, to_play = player_tables(int(search.get("number_of_player", 1)), search.get("custom_loop"), self.N + 2)
         self.to_play_table = to_play
