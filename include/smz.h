@@ -184,6 +184,14 @@ int smz_net_eval(smz_engine* e, int32_t which, int32_t n_rows, const float* in_d
  * rewards float[n][A].  Any pointer may be NULL. */
 int smz_read_roots(smz_engine* e, int32_t* visits_dev, float* root_values_dev, double* priors_dev,
                    float* rewards_dev, void* stream);
+/* The step after the search (game.py:179-235), on the device so that B games advance without a host
+ * round-trip: stored_policy double[n][A] = visit distribution (priors when fewer than 3 visits,
+ * store_search_statistics); policy double[n][A] = visits (priors when <= 1 visit) ** (1/temperature) only
+ * if temperature >= 0.3, normalised (softmax_stable); actions int32[n] = sampled from `policy` when
+ * temperature > 0.1 or the policy is flat, else first argmax (select_action).  uniforms_dev: double[n]
+ * recorded draws, or NULL for device Philox (stream 2).  Any output may be NULL. */
+int smz_select_actions(smz_engine* e, double temperature, const double* uniforms_dev, int32_t* actions_dev,
+                       double* policy_dev, double* stored_policy_dev, void* stream);
 /* Synchronises `stream`, then copies one tree to host memory. */
 int smz_export_tree(smz_engine* e, int32_t tree, smz_tree_host* out, void* stream);
 /* Hidden state of a slot (0 = root, s+1 = node expanded by simulation s): float[n][hidden_stride]. */

@@ -188,6 +188,39 @@ def dump_reference_tree(root, min_max_stats):
     return out, types
 
 
+READOUT_TEMPERATURES = (0.0, 0.0625, 0.2, 0.25, 0.3, 0.5, 0.7, 1.0, 2.0, 3.0)
+
+
+def reference_readout(root, seed):
+    """The reference's own read-out of a searched root (game.py:179-216) for a set of temperatures, with the
+    uniform behind np.random.choice recorded.  Uses Game's methods on a bare instance."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sys.path.insert(0, ref_shim.REFERENCE_DIR)
+        try:
+            import game as ref_game
+        finally:
+            sys.path.remove(ref_shim.REFERENCE_DIR)
+    g = ref_game.Game.__new__(ref_game.Game)
+    g.child_visits, g.root_values = [], []
+    g.store_search_statistics(root)
+    out = {"stored": np.asarray(g.child_visits[0], np.float64), "root_value": np.float32(g.root_values[0]),
+           "policy": [], "index": [], "u": [], "sampled": []}
+    keys = list(root.children.keys())
+    for t_i, T in enumerate(READOUT_TEMPERATURES):
+        action, policy, _reward = g.policy_action_reward_from_tree(root)
+        policy = g.softmax_stable(policy, temperature=T)
+        rr = RecordingRandom(seed * 131 + t_i)
+        with rr.patched():
+            sel = g.select_action(action, policy, T)
+        out["policy"].append(np.asarray(policy, np.float64))
+        out["index"].append(keys.index(sel))
+        out["u"].append(rr.uniforms[0] if rr.uniforms else 0.5)
+        out["sampled"].append(len(rr.uniforms) > 0)
+    return out
+
+
 def record_run(mcts_kwargs, model, seed, train=True, obs=None, prior_runs=0):
     """Run the reference search once and return (tape, expected) dicts."""
     ref_mcts, _ = ref_shim.load()
@@ -255,6 +288,7 @@ def record_run(mcts_kwargs, model, seed, train=True, obs=None, prior_runs=0):
         "sim_branch": sim_branch, "sim_action": sim_action,
     }
     expected["paths"] = paths
+    expected["readout"] = reference_readout(root, seed)
     extra = {"root_hidden": calls[0][1], "sim_hidden": hidden, "types": sorted(types)}
     return tape, expected, extra
 
@@ -285,6 +319,14 @@ def pack_batch(cfg, train, runs):
     out["exp_minmax"] = np.zeros((B, 2), np.float32)
     out["exp_root_to_play"] = np.zeros(B, np.int32)
     out["exp_paths"] = np.full((B, N, Lmax), -1, np.int32)
+    nT = len(READOUT_TEMPERATURES)
+    out["readout_temperature"] = np.array(READOUT_TEMPERATURES, np.float64)
+    out["readout_stored"] = np.zeros((B, A), np.float64)
+    out["readout_root_value"] = np.zeros(B, np.float32)
+    out["readout_policy"] = np.zeros((B, nT, A), np.float64)
+    out["readout_index"] = np.zeros((B, nT), np.int32)
+    out["readout_u"] = np.zeros((B, nT), np.float64)
+    out["readout_sampled"] = np.zeros((B, nT), np.int8)
     for b, (t, e) in enumerate(runs):
         u = t["uniforms"]
         out["uniforms"][b, :len(u)] = u
@@ -305,6 +347,10 @@ def pack_batch(cfg, train, runs):
         out["exp_root_to_play"][b] = e["root_to_play"]
         for s, p in enumerate(e["paths"]):
             out["exp_paths"][b, s, :len(p)] = p
+        ro = e["readout"]
+        out["readout_stored"][b], out["readout_root_value"][b] = ro["stored"], ro["root_value"]
+        out["readout_policy"][b] = np.stack(ro["policy"])
+        out["readout_index"][b], out["readout_u"][b], out["readout_sampled"][b] = ro["index"], ro["u"], ro["sampled"]
     return out
 
 

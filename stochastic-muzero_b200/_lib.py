@@ -63,6 +63,7 @@ SIGNATURES = {
     "smz_expand_backup": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "smz_net_eval": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "smz_read_roots": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "smz_select_actions": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "smz_export_tree": (C.c_int, [_P, C.c_int32, C.POINTER(smz_tree_host), _P]),
     "smz_read_hidden": (C.c_int, [_P, C.c_int32, _P, _P]),
     "smz_read_record": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),

@@ -445,6 +445,18 @@ int smz_read_roots(smz_engine* e, int32_t* visits, float* values, double* priors
   return SMZ_OK;
 }
 
+int smz_select_actions(smz_engine* e, double temperature, const double* uniforms, int32_t* actions, double* policy,
+                       double* stored_policy, void* stream) {
+  if (!e) return fail(SMZ_E_INVALID_ARG, "smz_select_actions: null engine");
+  if (e->n_trees < 1) return fail(SMZ_E_STATE, "smz_select_actions: smz_root has not been called");
+  if (!(temperature >= 0.0)) return fail(SMZ_E_INVALID_ARG, "smz_select_actions: temperature must be >= 0");
+  CU(cudaSetDevice(e->cfg.device));
+  smz_launch_select_actions(e->a, e->n_trees, temperature, uniforms, actions, policy, stored_policy, (cudaStream_t)stream);
+  e->launches += 1;
+  CU(cudaGetLastError());
+  return SMZ_OK;
+}
+
 int smz_export_tree(smz_engine* e, int32_t tree, smz_tree_host* out, void* stream) {
   if (!e || !out) return fail(SMZ_E_INVALID_ARG, "smz_export_tree: null argument");
   if (tree < 0 || tree >= e->n_trees) return fail(SMZ_E_INVALID_ARG, "smz_export_tree: tree %d not in [0, %d)", tree, e->n_trees);

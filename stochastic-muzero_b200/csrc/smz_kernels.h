@@ -17,6 +17,8 @@ void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,
                            cudaStream_t s);
 void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s);
+void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperature, const double* u, int* actions,
+                               double* policy, double* stored, cudaStream_t s);
 
 // ---- network (smz_net_f32.cu / smz_net_bf16.cu) --------------------------------------------------
 // Model shape and the padded fp32 weight image the CUDA-core path reads (built by smz_net_pack).

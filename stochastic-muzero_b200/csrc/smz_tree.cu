@@ -401,6 +401,70 @@ __global__ void k_read_roots(SmzArena a, int n_trees, int* __restrict__ visits, 
   }
 }
 
+// numpy float64 add.reduce order over a small local array (same pairwise scheme as np_sum_f32)
+__device__ double np_sum_f64(const double* x, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r = __dadd_rn(r, x[i]);
+    return r;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = x[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], x[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, x[i]);
+  return res;
+}
+
+// The step after the search, one thread per tree (game.py:179-216): the policy stored as training target
+// (`store_search_statistics`), the temperature-scaled acting policy (`policy_action_reward_from_tree` +
+// `softmax_stable`) and the action (`select_action`: sample when T > 0.1 or the policy is flat, else argmax).
+__global__ void k_select_actions(SmzArena a, int n_trees, double temperature, const double* __restrict__ u_in,
+                                 int* __restrict__ action_out, double* __restrict__ policy_out,
+                                 double* __restrict__ stored_out) {
+  const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= n_trees) return;
+  const size_t tb = (size_t)tree * a.M;
+  const int n = a.A;
+  double v[SMZ_MAX_POLICY], pr[SMZ_MAX_POLICY], p[SMZ_MAX_POLICY];
+  for (int i = 0; i < n; ++i) {
+    v[i] = (double)a.stat[tb + 1 + i].x;
+    pr[i] = a.root_prior[(size_t)tree * n + i];
+  }
+  const double sv = np_sum_f64(v, n);
+  if (stored_out) {
+    const double sp = np_sum_f64(pr, n);
+    for (int i = 0; i < n; ++i) stored_out[(size_t)tree * n + i] = sv >= 3.0 ? __ddiv_rn(v[i], sv) : __ddiv_rn(pr[i], sp);
+  }
+  const double e = 1.0 / temperature;
+  for (int i = 0; i < n; ++i) {
+    double x = sv <= 1.0 ? pr[i] : v[i];
+    if (temperature >= 0.3) x = e == 1.0 ? x : (e == 2.0 ? __dmul_rn(x, x) : (e == 0.5 ? sqrt(x) : pow(x, e)));
+    p[i] = x;
+  }
+  const double s = np_sum_f64(p, n);
+  bool flat = true;
+  for (int i = 0; i < n; ++i) {
+    p[i] = __ddiv_rn(p[i], s);
+    flat = flat && p[i] == p[0];
+    if (policy_out) policy_out[(size_t)tree * n + i] = p[i];
+  }
+  int pick = 0;
+  if (temperature > 0.1 || flat) {
+    const double u = u_in ? u_in[tree] : smz_philox_uniform(a.seed_state[0], a.seed_state[1] + (unsigned long long)tree, 0u, 2u);
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) { acc = __dadd_rn(acc, p[i]); v[i] = acc; }
+    for (int i = 0; i < n; ++i) pick += __ddiv_rn(v[i], acc) <= u;
+    pick = pick < n ? pick : n - 1;
+  } else {
+    for (int i = 1; i < n; ++i) if (p[i] > p[pick]) pick = i;
+  }
+  if (action_out) action_out[tree] = a.link[tb + 1 + pick].y;
+}
+
 // Dirichlet(alpha) per tree on the device: Gamma(alpha) by Marsaglia-Tsang (alpha+1 boost), Philox
 // stream 1.  Production mode only; parity runs pass recorded noise (np.random.dirichlet, mcts.py:220).
 __global__ void k_dirichlet(SmzArena a, int n_trees) {
@@ -472,6 +536,11 @@ void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* v
                            cudaStream_t s) {
   const int n = n_trees * a.A;
   k_read_roots<<<(n + 255) / 256, 256, 0, s>>>(a, n_trees, visits, values, priors, rewards);
+}
+
+void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperature, const double* u, int* actions,
+                               double* policy, double* stored, cudaStream_t s) {
+  k_select_actions<<<(n_trees + 127) / 128, 128, 0, s>>>(a, n_trees, temperature, u, actions, policy, stored);
 }
 
 void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s) {

@@ -251,6 +251,16 @@ class SearchEngine:
                                             self._ptr(out.get("priors")), self._ptr(out.get("rewards")), self._stream))
         return out
 
+    def select_actions(self, temperature: float, uniforms=None):
+        """game.py:179-235 for every tree: -> dict(actions int32[n], policy f64[n,A], stored_policy f64[n,A])."""
+        n, A = self.n_trees, self.A
+        u = self._dev(uniforms, torch.float64, "readout_u")
+        out = {"actions": self._new(n, dtype=torch.int32), "policy": self._new(n, A, dtype=torch.float64),
+               "stored_policy": self._new(n, A, dtype=torch.float64)}
+        self._check(self.lib.smz_select_actions(self._h, float(temperature), self._ptr(u), self._ptr(out["actions"]),
+                                                self._ptr(out["policy"]), self._ptr(out["stored_policy"]), self._stream))
+        return out
+
     def read_hidden(self, slot):
         out = self._new(self.n_trees, self.dims.hidden_stride, dtype=torch.float32)
         self._check(self.lib.smz_read_hidden(self._h, int(slot), self._ptr(out), self._stream))

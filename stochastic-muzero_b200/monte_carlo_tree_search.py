@@ -153,6 +153,11 @@ class BatchedRoots:
     def __len__(self):
         return int(self.visit_counts.shape[0])
 
+    def select_actions(self, temperature: float = 0.0, uniforms=None):
+        """Batched Game.policy_step / store_search_statistics (game.py:179-235) on the device:
+        dict(actions, policy, stored_policy); root values are `self.root_values`."""
+        return self._engine.select_actions(temperature, uniforms)
+
     def __getitem__(self, i) -> Node:
         return _node_tree(self._engine.export_tree(int(i)), self._hidden_fetcher(int(i)))
 

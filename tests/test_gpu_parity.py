@@ -384,3 +384,72 @@ def test_wide_chance_codebook_full_search_config3_shape():
             golden_io.assert_dump_equal(eng.export_tree(b), tree.dump(), f"cfg3-{net}[{b}]")
         assert (eng.read_roots()["visits"].sum(1) == 100).all()
         eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the step after the search: device read-out + action selection vs game.py:179-235
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_io.tree_cases())
+def test_device_action_selection_matches_reference_policy_step(name):
+    z = golden_io.load_tree_case(name)
+    eng, _, _ = _replay_tape(z)
+    for t_i, T in enumerate(z["readout_temperature"]):
+        out = eng.select_actions(float(T), uniforms=torch.from_numpy(z["readout_u"][:, t_i].copy()))
+        pol = out["policy"].cpu().numpy()
+        e = 1.0 / T if T >= 0.3 else 1.0
+        if e in (1.0, 2.0, 0.5):          # exact arithmetic on both sides
+            assert np.array_equal(pol, z["readout_policy"][:, t_i]), f"T={T}"
+        else:                             # pow(): libm vs CUDA, <= 2 ulp
+            np.testing.assert_allclose(pol, z["readout_policy"][:, t_i], rtol=1e-14, atol=0)
+        assert np.array_equal(out["actions"].cpu().numpy(), z["readout_index"][:, t_i]), f"T={T}: selected actions"
+        assert np.array_equal(out["stored_policy"].cpu().numpy(), z["readout_stored"])
+    assert np.array_equal(eng.read_roots()["root_values"].cpu().numpy(), z["readout_root_value"])
+    eng.close()
+
+
+def test_full_size_4096_trees_50_simulations_properties_and_sampled_replay():
+    """BASELINE configs[1] at full size in throughput mode.  Size-independent properties for all trees,
+    and an oracle replay (bit-exact) of a sample of them from the engine's own record."""
+    from stochastic_muzero_b200 import ModelShape, SearchEngine
+    from stochastic_muzero_b200.weights import random_blob
+    shape = ModelShape(4, 2, 2, 61, 126, 4)
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=50, maxium_action_sample=2,
+                  number_of_player=1, custom_loop=None)
+    B, N, seed = 4096, 50, 2024
+    eng = SearchEngine(search, 2, 2, max_trees=B, model_shape=shape, net="bf16", rng="philox", seed=seed, record=True)
+    eng.set_weights(random_blob(shape, seed=0))
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(0))
+    eng.root(obs=obs, train=True)
+    eng.simulate(N)
+    st = eng.stats()
+    roots = {k: v.cpu().numpy() for k, v in eng.read_roots().items()}
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    # properties: every simulation visits the root once and exactly one root child
+    assert (roots["visits"].sum(1) == N).all() and (roots["visits"] >= 0).all()
+    assert np.allclose(roots["priors"].sum(1), 1.0, atol=1e-6) and (roots["priors"] > 0).all()
+    assert np.isfinite(roots["root_values"]).all()
+    # root value = mean of N discounted returns, each bounded by sum_k gamma^k max|r| + gamma^d max|v|
+    bound = (np.abs(rec["sim_reward"]).max() / (1 - 0.997) + np.abs(rec["sim_value"]).max())
+    assert (np.abs(roots["root_values"]) <= bound).all()
+    assert np.allclose(rec["sim_policy"].sum(2), 1.0, atol=1e-5)
+    assert set(np.unique(rec["sim_branch"])) <= {0, 1} and (rec["sim_branch"][:, 0] == 0).all()
+    assert (rec["sim_reward"][rec["sim_branch"] == 0] == 0).all()
+    assert 2.0 < st["mean_leaf_depth"] < 10.0
+    # same seed twice => identical statistics (graph replay, atomics only order rows)
+    eng.set_seed(seed); eng.root(obs=obs, train=True); eng.simulate(N)
+    again = eng.read_roots()
+    assert np.array_equal(again["visits"].cpu().numpy(), roots["visits"])
+    assert np.array_equal(again["root_values"].cpu().numpy(), roots["root_values"])
+    # sampled oracle replay
+    cfg = O.SearchConfig(**search)
+    for b in np.random.default_rng(0).choice(B, 24, replace=False):
+        model = O.TapeModel(rec["root_policy"][b, :2], rec["sim_policy"][b], np.full(N, 2), rec["sim_value"][b],
+                            rec["sim_reward"][b])
+        tree = O.search(cfg, model, O.PhiloxUniforms(seed, int(b)), train=True, dirichlet=rec["dirichlet"][b])
+        golden_io.assert_dump_equal(eng.export_tree(int(b)), tree.dump(), f"full-size[{b}]")
+    # device action selection on all trees: argmax at T = 0 equals numpy's
+    act = eng.select_actions(0.0)["actions"].cpu().numpy()
+    flat = roots["visits"][:, 0] == roots["visits"][:, 1]
+    assert np.array_equal(act[~flat], roots["visits"].argmax(1)[~flat])
+    eng.close()

@@ -63,3 +63,23 @@ def test_net_oracle_matches_reference_inference(name):
     np.testing.assert_allclose(probs, z["enc_probs"], atol=NET_TOL, rtol=0)
     margin = np.abs(z["enc_probs"][:, :1] - z["enc_probs"]).max(axis=1) if z["enc_probs"].shape[1] == 2 else None
     assert np.array_equal(code, z["enc_code"]) or margin is not None and (margin[code != z["enc_code"]] < 1e-5).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# read-out / action selection oracle vs the reference's Game methods (game.py:179-216)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_io.tree_cases())
+def test_readout_oracle_matches_reference_game_methods(name):
+    from oracle import readout_oracle as RO
+    z = golden_io.load_tree_case(name)
+    A = z["config"]["action_dim"]
+    for b in range(len(z["n_nodes"])):
+        e = golden_io.expected_dump(z, b)
+        kids = np.flatnonzero(e["depth"] == 1)
+        visits, priors = e["visit"][kids], e["prior"][kids]
+        assert np.array_equal(RO.stored_policy(visits, priors), z["readout_stored"][b])
+        for t_i, T in enumerate(z["readout_temperature"]):
+            pol = RO.step_policy(visits, priors, T)
+            assert np.array_equal(pol, z["readout_policy"][b, t_i])
+            idx, sampled = RO.select_action(pol, T, z["readout_u"][b, t_i])
+            assert sampled == bool(z["readout_sampled"][b, t_i]) and idx == z["readout_index"][b, t_i]
