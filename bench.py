@@ -42,7 +42,7 @@ def tree_bytes_per_sim(depth, K, S):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -50,12 +50,14 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(device)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons over the samples taken inside [t0, t1] (epoch seconds)."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -67,13 +69,16 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
@@ -155,7 +160,9 @@ def main():
     blob = torch.from_numpy(random_blob(shape, seed=0)).to(dev) if rank == 0 else \
         torch.empty(eng.dims.weight_blob_floats, dtype=torch.float32, device=dev)
     bcast_ms = 0.0
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi takes a while to spin up
     if world > 1:
+        dist.all_reduce(torch.zeros(1, device=dev))           # NCCL communicator set-up is not the broadcast
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         dist.broadcast(blob, src=0)
@@ -177,7 +184,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    wall0 = time.time()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     for i, (a, b) in enumerate(evs):
@@ -190,7 +197,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, time.time()) if sampler else None
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -29,7 +29,7 @@ struct SmzArena {
   int* ucursor;
   int* root_to_play;
   // per-simulation scratch
-  int* path;        // [B][path_stride] node indices root..leaf
+  int4* path;       // [B][path_stride] per level {node, visit_count, value_sum, reward} captured by the descent
   int* path_len;    // [B]
   int* leaf_node;   // [B]
   int* leaf_slot;   // [B] hidden slot of search_path[-2]
@@ -109,11 +109,25 @@ __device__ __forceinline__ double smz_philox_uniform(unsigned long long seed, un
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-__device__ __forceinline__ double smz_uniform(const SmzArena& a, int tree, int idx) {
-  if (a.rng_mode) {
-    if (idx >= a.tape_stride) { *a.error_flag = 1; return 0.5; }
-    return a.tape_u[(size_t)tree * a.tape_stride + idx];
+// per-thread view of the uniform source: the Philox key is read from device memory ONCE per kernel
+struct SmzRng {
+  int mode, stride;
+  const double* tape;
+  unsigned long long seed, tree0;
+  int* err;
+};
+__device__ __forceinline__ SmzRng smz_make_rng(const SmzArena& a) {
+  SmzRng r;
+  r.mode = a.rng_mode; r.stride = a.tape_stride; r.tape = a.tape_u; r.err = a.error_flag;
+  r.seed = a.rng_mode ? 0ull : a.seed_state[0];
+  r.tree0 = a.rng_mode ? 0ull : a.seed_state[1];
+  return r;
+}
+__device__ __forceinline__ double smz_rng_uniform(const SmzRng& r, int tree, int idx) {
+  if (r.mode) {
+    if (idx >= r.stride) { *r.err = 1; return 0.5; }
+    return r.tape[(size_t)tree * r.stride + idx];
   }
-  return smz_philox_uniform(a.seed_state[0], a.seed_state[1] + (unsigned long long)tree, (unsigned)idx, 0u);
+  return smz_philox_uniform(r.seed, r.tree0 + (unsigned long long)tree, (unsigned)idx, 0u);
 }
 #endif

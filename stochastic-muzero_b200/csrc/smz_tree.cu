@@ -95,8 +95,8 @@ __device__ float normalise_policy(const Group<G>& g, float pol, int n) {
 // np.random.choice(n, bound, p=p, replace=False): returns the bit set of chosen indices and advances
 // the tree's uniform cursor by the number of draws numpy would have consumed.
 template <int G>
-__device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, bool alive, int tree, float p32,
-                                               int n, int bound, int& cursor) {
+__device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, const SmzRng& rng, bool alive, int tree,
+                                               float p32, int n, int bound, int& cursor) {
   unsigned found = 0;
   int nf = alive ? 0 : bound;
   const double pd = (g.gl < n) ? (double)p32 : 0.0;
@@ -113,7 +113,7 @@ __device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena
     const double c = choice_cdf(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n);
     for (int j = 0; __any_sync(FULL, j < m); ++j) {
       const bool on = j < m;
-      const double u = on ? smz_uniform(a, tree, cursor + j) : 0.0;
+      const double u = on ? smz_rng_uniform(rng, tree, cursor + j) : 0.0;
       int idx = __popc(g.ballot(c <= u));
       idx = idx < n ? idx : n - 1;
       if (on && !((found >> idx) & 1u)) { found |= 1u << idx; ++nf; }
@@ -138,7 +138,8 @@ __global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__
   const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
   const float p = normalise_policy(g, pol, n);
   // all A actions become children (ascending); the call still consumes its draws (T5)
-  choice_without_replacement(g, a, alive, tree, p, n, n, cursor);
+  const SmzRng rng = smz_make_rng(a);
+  choice_without_replacement(g, a, rng, alive, tree, p, n, n, cursor);
   if (!alive) return;
   if (g.gl < n) {
     double prior = (double)p;
@@ -163,19 +164,28 @@ __global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-tree state that flows from the backup of one simulation into the descent of the next.  The fused
+// kernel keeps it in registers; the stand-alone kernels load / store it.
+struct TreeState {
+  int cursor;      // uniform draws consumed so far
+  float2 mm;       // MinMaxStats
+  int2 root;       // root {visit_count, value_sum bits}
+};
+
+// The search path is kept as one int4 record per level {node, visit_count, value_sum, reward} captured
+// while descending, so the backup needs ONE round trip (the record) instead of two (index -> stat).
 template <int G>
-__device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, int tree, bool alive, int sim,
-                                             int* __restrict__ o_slot, int* __restrict__ o_action,
+__device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree, bool alive,
+                                             int sim, TreeState ts, int* __restrict__ o_slot, int* __restrict__ o_action,
                                              int* __restrict__ o_branch) {
   const size_t tb = (size_t)tree * a.M;
-  int cursor = a.ucursor[tree];
-  const float2 mm = a.minmax[tree];
-  const float vmin = mm.x, vmax = mm.y;
-  int* path = a.path + (size_t)tree * a.path_stride;
+  int cursor = ts.cursor;
+  const float vmin = ts.mm.x, vmax = ts.mm.y;
+  int4* path = a.path + (size_t)tree * a.path_stride;
 
   int depth = 0, cbase = 1, nch = a.A;
-  int parent_visit = a.stat[tb].x;
-  if (alive && g.gl == 0) path[0] = 0;
+  int parent_visit = ts.root.x;
+  if (alive && g.gl == 0) path[0] = make_int4(0, ts.root.x, ts.root.y, 0);
   int L = 1, child = 0, child_key = 0;
   bool going = alive;
   while (__any_sync(FULL, going)) {
@@ -183,7 +193,15 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     const bool chance = (depth >> 1) & 1;
     int4 st = make_int4(0, 0, 0, 0);
     int2 lk = make_int2(0, 0);
-    if (act) { st = a.stat[tb + cbase + g.gl]; lk = a.link[tb + cbase + g.gl]; }
+    double prior0 = 0.0, pbc = 0.0;
+    if (act) {
+      st = a.stat[tb + cbase + g.gl];
+      lk = a.link[tb + cbase + g.gl];
+      if (depth == 0) prior0 = a.root_prior[(size_t)tree * a.A + g.gl];
+      if (!chance) pbc = __ldg(a.pbc + parent_visit);
+    }
+    // the draw only depends on the cursor: it is computed while the loads are in flight
+    const double u = (going && (chance || act)) ? smz_rng_uniform(rng, tree, chance ? cursor : cursor + g.gl) : 0.0;
     int pick = 0;
     if (__any_sync(FULL, going && chance)) {
       // chance node: sample a child from the smoothed priors (mcts.py:249-255, T9)
@@ -194,7 +212,6 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       const float tot = np_sum_f32(g, sh, nch);
       const float q = act ? __fdiv_rn(sh, tot) : 0.f;
       const double c = choice_cdf(g, (double)q, nch);
-      const double u = (going && chance) ? smz_uniform(a, tree, cursor) : 0.0;
       int pk = __popc(g.ballot(act && c <= u));
       pk = pk < nch ? pk : nch - 1;
       if (chance) { pick = pk; cursor += going ? 1 : 0; }
@@ -204,10 +221,9 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       double score = -__longlong_as_double(0x7ff0000000000000LL);
       int best = -1;
       if (act && !chance) {
-        const double prior = (depth == 0) ? a.root_prior[(size_t)tree * a.A + g.gl] : (double)__int_as_float(st.w);
-        const double u = smz_uniform(a, tree, cursor + g.gl);
-        // a.pbc[n] = sqrt(n) * pb_c(n), the left-associated head of mcts.py:237, tabulated by the host
-        const double ps = __ddiv_rn(__dmul_rn(a.pbc[parent_visit], prior), (double)(st.x + 1));
+        const double prior = (depth == 0) ? prior0 : (double)__int_as_float(st.w);
+        // pbc = sqrt(n) * pb_c(n), the left-associated head of mcts.py:237, tabulated by the host
+        const double ps = __ddiv_rn(__dmul_rn(pbc, prior), (double)(st.x + 1));
         double vs = 0.0;
         if (st.x > 0) {
           const float val = __fdiv_rn(__int_as_float(st.y), (float)st.x);
@@ -227,20 +243,20 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       }
       if (!chance) { pick = best < 0 ? 0 : best; cursor += going ? nch : 0; }
     }
-    const int child_visit = g.bcast(st.x, pick);
+    const int4 cst = make_int4(g.bcast(st.x, pick), g.bcast(st.y, pick), g.bcast(st.z, pick), 0);
     const int child_cb = g.bcast(lk.x, pick);
     const int key = g.bcast(lk.y, pick);
     if (going) {
       child = cbase + pick;
       child_key = key;
-      if (g.gl == 0) path[L] = child;
+      if (g.gl == 0) path[L] = make_int4(child, cst.x, cst.y, cst.z);
       ++L;
       if (child_cb == 0 || L >= a.path_stride) {
         going = false;
       } else {
         // the child (depth+1) was expanded through the dynamics pair iff this node is a chance node (T2)
         nch = chance ? a.Kd : a.Kc;
-        parent_visit = child_visit;
+        parent_visit = cst.x;
         cbase = child_cb;
         ++depth;
       }
@@ -267,33 +283,42 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
 
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ void expand_backup_phase(const Group<G>& g, const SmzArena& a, int tree, bool alive, int sim,
-                                                    const float* __restrict__ policy, int pstride,
-                                                    const float* __restrict__ value, const float* __restrict__ reward) {
+__device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree,
+                                                         bool alive, int sim, const float* __restrict__ policy,
+                                                         int pstride, const float* __restrict__ value,
+                                                         const float* __restrict__ reward) {
   const size_t tb = (size_t)tree * a.M;
+  // everything this phase needs from memory is requested up front (one round trip): the leaf record,
+  // the network outputs, the tree state and — speculatively — the first two chunks of path records
+  const int4* path = a.path + (size_t)tree * a.path_stride;
+  const int4 rec0 = (g.gl < a.path_stride) ? path[g.gl] : make_int4(0, 0, 0, 0);
+  const int4 rec1 = (G + g.gl < a.path_stride) ? path[G + g.gl] : make_int4(0, 0, 0, 0);
   const int leaf = a.leaf_node[tree];
   const int branch = a.leaf_branch[tree];
   const int L = alive ? a.path_len[tree] : 0;
   int cursor = a.ucursor[tree];
-  const int* path = a.path + (size_t)tree * a.path_stride;
+  float2 mm = a.minmax[tree];
+  float v = value[tree];
+  const float rew_in = reward[tree];
+  const signed char* sign = a.sign + (size_t)a.root_to_play[tree] * (a.N + 2);
 
   // children of the leaf (mcts.py:289-297): width C after the afterstate pair, A after dynamics
   const int n = branch ? a.A : a.C;
   const int bound = min(a.K, n);
   const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
   const float p = normalise_policy(g, pol, n);
-  const unsigned found = choice_without_replacement(g, a, alive, tree, p, n, bound, cursor);
+  const unsigned found = choice_without_replacement(g, a, rng, alive, tree, p, n, bound, cursor);
   const int cb = 1 + a.A + sim * a.Kmax;
   if (alive && g.gl < n && ((found >> g.gl) & 1u)) {
     const int r = __popc(found & ((1u << g.gl) - 1u));
     a.stat[tb + cb + r] = make_int4(0, 0, 0, __float_as_int(p));
     a.link[tb + cb + r] = make_int2(0, g.gl);
   }
-  float v = value[tree];
-  const float rew = branch ? reward[tree] : 0.f;
+  const float rew = branch ? rew_in : 0.f;
   if (alive && g.gl == 0) {
     a.link[tb + leaf].x = cb;
     a.ucursor[tree] = cursor;
+    if (branch) reinterpret_cast<int*>(a.stat + tb + leaf)[2] = __float_as_int(rew);     // Node.reward of the leaf
     if (a.rec_policy) {
       const size_t ro = ((size_t)tree * a.N + sim);
       for (int i = 0; i < a.W; ++i) a.rec_policy[ro * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
@@ -305,22 +330,18 @@ __device__ __forceinline__ void expand_backup_phase(const Group<G>& g, const Smz
 
   // backup leaf -> root (mcts.py:299-308): lanes own path levels, the discounted return is a serial
   // float32 recurrence (mul then add, two roundings) carried through shuffles
-  const signed char* sign = a.sign + (size_t)a.root_to_play[tree] * (a.N + 2);
-  float2 mm = a.minmax[tree];
+  int2 root = make_int2(0, 0);
   int n_chunks = (L + G - 1) / G;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) n_chunks = max(n_chunks, __shfl_xor_sync(FULL, n_chunks, off));
   for (int chunk = n_chunks - 1; chunk >= 0; --chunk) {
     const int l = chunk * G + g.gl;
     const bool valid = l < L;
-    int node = 0;
-    int4 st = make_int4(0, 0, 0, 0);
-    if (valid) {
-      node = path[l];
-      st = a.stat[tb + node];
-      if (l == L - 1 && branch) st.z = __float_as_int(rew);
-    }
-    const float r = __int_as_float(st.z);
+    int4 rec = chunk == 0 ? rec0 : rec1;
+    if (chunk > 1 && valid) rec = path[l];
+    if (!valid) rec = make_int4(0, 0, 0, 0);
+    if (valid && l == L - 1 && branch) rec.w = __float_as_int(rew);
+    const float r = __int_as_float(rec.w);
     float myv = 0.f;
 #pragma unroll
     for (int t = G - 1; t >= 0; --t) {
@@ -331,11 +352,11 @@ __device__ __forceinline__ void expand_backup_phase(const Group<G>& g, const Smz
       }
     }
     if (valid) {
-      const float vs = __fadd_rn(__int_as_float(st.y), sign[l] > 0 ? myv : -myv);
-      st.x += 1;
-      st.y = __float_as_int(vs);
-      a.stat[tb + node] = st;
-      const float nv = __fdiv_rn(vs, (float)st.x);
+      const float vs = __fadd_rn(__int_as_float(rec.z), (signed char)__ldg(sign + l) > 0 ? myv : -myv);
+      const int2 upd = make_int2(rec.y + 1, __float_as_int(vs));
+      *reinterpret_cast<int2*>(a.stat + tb + rec.x) = upd;          // {visit_count, value_sum}
+      if (l == 0) root = upd;
+      const float nv = __fdiv_rn(vs, (float)upd.x);
       mm.x = fminf(mm.x, nv);
       mm.y = fmaxf(mm.y, nv);
     }
@@ -346,6 +367,11 @@ __device__ __forceinline__ void expand_backup_phase(const Group<G>& g, const Smz
     mm.y = fmaxf(mm.y, __shfl_xor_sync(FULL, mm.y, off, G));
   }
   if (alive && g.gl == 0) a.minmax[tree] = mm;
+  TreeState ts;
+  ts.cursor = cursor;
+  ts.mm = mm;
+  ts.root = make_int2(g.bcast(root.x, 0), g.bcast(root.y, 0));   // level 0 lives in lane 0 of chunk 0
+  return ts;
 }
 
 template <int G>
@@ -355,7 +381,13 @@ __global__ void k_select(SmzArena a, int n_trees, int sim, int* __restrict__ o_s
   int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool alive = tree < n_trees;
   if (!alive) tree = n_trees - 1;
-  select_phase(g, a, tree, alive, sim, o_slot, o_action, o_branch);
+  const SmzRng rng = smz_make_rng(a);
+  TreeState ts;
+  ts.cursor = a.ucursor[tree];
+  ts.mm = a.minmax[tree];
+  const int4 rs = a.stat[(size_t)tree * a.M];
+  ts.root = make_int2(rs.x, rs.y);
+  select_phase(g, a, rng, tree, alive, sim, ts, o_slot, o_action, o_branch);
 }
 
 template <int G>
@@ -365,7 +397,8 @@ __global__ void k_expand_backup(SmzArena a, int n_trees, int sim, const float* _
   int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool alive = tree < n_trees;
   if (!alive) tree = n_trees - 1;
-  expand_backup_phase(g, a, tree, alive, sim, policy, pstride, value, reward);
+  const SmzRng rng = smz_make_rng(a);
+  expand_backup_phase(g, a, rng, tree, alive, sim, policy, pstride, value, reward);
 }
 
 // expansion + backup of simulation `sim` followed by the descent of simulation `sim + 1` for the same
@@ -379,9 +412,10 @@ __global__ void k_backup_select(SmzArena a, int n_trees, int sim) {
   int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool alive = tree < n_trees;
   if (!alive) tree = n_trees - 1;
-  expand_backup_phase(g, a, tree, alive, sim, a.out_policy, a.W, a.out_value, a.out_reward);
+  const SmzRng rng = smz_make_rng(a);
+  const TreeState ts = expand_backup_phase(g, a, rng, tree, alive, sim, a.out_policy, a.W, a.out_value, a.out_reward);
   __syncwarp();
-  select_phase(g, a, tree, alive, sim + 1, nullptr, nullptr, nullptr);
+  select_phase(g, a, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
