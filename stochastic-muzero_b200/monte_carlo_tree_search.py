@@ -21,6 +21,7 @@ from typing import Optional
 import numpy as np
 import torch
 
+from . import batched_model
 from .engine import SearchEngine, _is_chance
 from .weights import PackedModel, pack_weights, shape_of, weights_version
 
@@ -285,8 +286,7 @@ class Monte_carlo_tree_search():
         """B independent searches in one call.  ``observations``: float tensor/array [B, obs_dim]
         (host or device).  Returns BatchedRoots (device tensors; ``roots[i]`` gives a Node view)."""
         if not self._is_fusable(model):
-            raise TypeError("run_batch needs a reference-style MLP Muzero (model_structure == 'mlp_model'); "
-                            "other models go through run(), one tree at a time")
+            return self._run_batch_external(observations, model, train, root_to_play)
         self.model = model
         shape = shape_of(model)
         obs = observations if torch.is_tensor(observations) else torch.as_tensor(np.asarray(observations))
@@ -301,6 +301,33 @@ class Monte_carlo_tree_search():
         eng.root(obs=obs, root_to_play=root_to_play, train=train)
         eng.simulate(self.num_simulations)
         return BatchedRoots(eng, eng.read_roots())
+
+    def _run_batch_external(self, observations, model, train, root_to_play):
+        """Any other model family: tree kernels in the engine, network step = five batched device
+        functions (batched_model.py) — either supplied directly or built from the six nn.Modules of a
+        reference-style Muzero."""
+        self.model = model
+        if batched_model.is_batched_backend(model):
+            backend = model
+        elif all(hasattr(model, f"{n}_function") for n in ("representation", "prediction", "afterstate_prediction",
+                                                           "afterstate_dynamics", "dynamics")):
+            key = ("backend", id(model))
+            backend = self._weights_seen.get(key)
+            if backend is None:
+                backend = self._weights_seen[key] = batched_model.ReferenceModuleBackend(
+                    model, device=f"cuda:{self._device if self._device is not None else torch.cuda.current_device()}")
+        else:
+            raise TypeError("run_batch needs a reference-style Muzero or an object with the five batched "
+                            "network functions (see batched_model.py)")
+        obs = observations if torch.is_tensor(observations) else torch.as_tensor(np.asarray(observations))
+        A = int(getattr(backend, "A", 0)) or int(getattr(model, "action_dimension"))
+        C = int(getattr(backend, "C", A))
+        eng, _ = self._engine("external", obs.shape[0], A, C)
+        eng.set_seed(self._next_seed())
+        store = batched_model.run_search(eng, backend, obs, self.num_simulations, root_to_play, train)
+        roots = BatchedRoots(eng, eng.read_roots())
+        roots.hidden_store = store
+        return roots
 
     def run(self, observation=None, model=None, train=True):
         """One search, reference signature (:311).  Returns the root Node."""

@@ -453,3 +453,77 @@ def test_full_size_4096_trees_50_simulations_properties_and_sampled_replay():
     flat = roots["visits"][:, 0] == roots["visits"][:, 1]
     assert np.array_equal(act[~flat], roots["visits"].argmax(1)[~flat])
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# external batched network back-end (any model family): tree kernels + torch modules
+# ---------------------------------------------------------------------------------------------------
+class _TorchMLPBackend:
+    """The MLP networks of a weight blob as plain batched torch ops on the GPU (what a non-fused model
+    family looks like to run_batch)."""
+
+    def __init__(self, blob, obs, A, C, S, H, L):
+        from stochastic_muzero_b200.batched_model import support_to_scalar
+        self._s2s = support_to_scalar
+        self.A, self.C, self.L, self.OH = A, C, L, max(A, C)
+        layout, _ = NO.blob_layout(obs, A, C, S, H, L)
+        b = torch.from_numpy(np.asarray(blob, np.float32)).cuda()
+        self.w = {k: b[o:o + int(np.prod(s))].reshape(s) for k, (o, s) in layout.items()}
+
+    def _lin(self, x, n):
+        return x @ self.w[n + ".w"].T + self.w[n + ".b"]
+
+    def _trunk(self, x, p):
+        x = torch.nn.functional.elu(self._lin(x, p + ".in"))
+        for _ in range(self.L):
+            x = torch.nn.functional.elu(self._lin(x, p + ".mid"))
+        return x
+
+    @staticmethod
+    def _scale(x):
+        lo, hi = x.min(1, keepdim=True)[0], x.max(1, keepdim=True)[0]
+        sc = hi - lo
+        sc = torch.where(sc < 1e-5, sc + 1e-5, sc)
+        return (x - lo) / sc
+
+    def representation(self, obs):
+        return self._scale(self._lin(self._trunk(obs.cuda().float(), "repr"), "repr.out"))
+
+    def _pred(self, h, p):
+        t = self._trunk(h, p)
+        return torch.softmax(self._lin(t, p + ".policy"), -1), self._s2s(self._lin(t, p + ".value"))
+
+    def prediction(self, h):
+        return self._pred(h, "pred")
+
+    def afterstate_prediction(self, h):
+        return self._pred(h, "apred")
+
+    def _cat(self, h, idx):
+        return torch.cat([h, torch.nn.functional.one_hot(idx.long(), self.OH).float()], 1)
+
+    def afterstate_dynamics(self, h, a):
+        return self._scale(self._lin(self._trunk(self._cat(h, a), "adyn"), "adyn.state"))
+
+    def dynamics(self, h, c):
+        t = self._trunk(self._cat(h, c), "dyn")
+        return self._s2s(self._lin(t, "dyn.reward")), self._scale(self._lin(t, "dyn.state"))
+
+
+def test_run_batch_with_external_batched_backend_matches_fused_engine():
+    from stochastic_muzero_b200 import Monte_carlo_tree_search, PackedModel, ModelShape
+    zn = golden_io.load_net_case("ckpt450")
+    dims = [int(v) for v in zn["dims"]]
+    backend = _TorchMLPBackend(zn["weights"], *dims)
+    kw = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+              root_exploration_fraction=0.25, num_simulations=30, maxium_action_sample=2, seed=5)
+    obs = torch.randn(200, 4, generator=torch.Generator().manual_seed(2))
+    ext = Monte_carlo_tree_search(**kw).run_batch(obs, backend, train=True)
+    fused = Monte_carlo_tree_search(**kw, net="fp32").run_batch(obs, PackedModel(zn["weights"], ModelShape(*dims)), train=True)
+    assert (ext.visit_counts.sum(1) == 30).all()
+    same = (ext.visit_counts == fused.visit_counts).all(1).float().mean().item()
+    assert same >= 0.97, f"only {same:.3f} of the trees agree between torch back-end and fused fp32 step"
+    agree = (ext.visit_counts == fused.visit_counts).all(1)
+    np.testing.assert_allclose(ext.root_values[agree].cpu().numpy(), fused.root_values[agree].cpu().numpy(),
+                               atol=1e-5, rtol=5e-5)
+    assert ext.hidden_store.shape == (31, 200, dims[3])
