@@ -33,6 +33,9 @@ def test_reference_module_backend_matches_reference_inference(family):
     else:
         mz = _vision_muzero()
         obs = torch.rand(3, 3, 98, 98)
+    # vision: scale_to_bound_action normalises over the 3 CHANNELS of each pixel (vision:495-503); when the
+    # three values nearly coincide the division amplifies fp32 noise (batched vs batch-1 conv algorithms)
+    hid_tol = 1e-5 if family == "mlp" else 2e-4
     be = ReferenceModuleBackend(mz, device="cpu")
     A = mz.action_dimension
     acts = torch.arange(obs.shape[0]) % A
@@ -44,15 +47,15 @@ def test_reference_module_backend_matches_reference_inference(family):
     with torch.no_grad():
         for i in range(obs.shape[0]):
             rh = mz.representation_function_inference(obs[i:i + 1])
-            np.testing.assert_allclose(h[i:i + 1].numpy(), rh.numpy(), atol=1e-5)
+            np.testing.assert_allclose(h[i:i + 1].numpy(), rh.numpy(), atol=hid_tol)
             rp, rv = mz.prediction_function_inference(rh)
             np.testing.assert_allclose(p[i].numpy(), rp[0], atol=1e-5)
             np.testing.assert_allclose(v[i].item(), rv, atol=1e-5, rtol=5e-5)
             rah = mz.afterstate_dynamics_function_inference(rh, int(acts[i]))
-            np.testing.assert_allclose(ah[i:i + 1].numpy(), rah.numpy(), atol=1e-5)
+            np.testing.assert_allclose(ah[i:i + 1].numpy(), rah.numpy(), atol=hid_tol)
             rap, rav = mz.afterstate_prediction_function_inference(rah)
             np.testing.assert_allclose(ap[i].numpy(), rap[0], atol=1e-5)
             np.testing.assert_allclose(av[i].item(), rav, atol=1e-5, rtol=5e-5)
             rr, rdh = mz.dynamics_function_inference(rah, int(acts[i]))
-            np.testing.assert_allclose(dh[i:i + 1].numpy(), rdh.numpy(), atol=1e-5)
+            np.testing.assert_allclose(dh[i:i + 1].numpy(), rdh.numpy(), atol=hid_tol)
             np.testing.assert_allclose(r[i].item(), rr, atol=1e-5, rtol=5e-5)
