@@ -362,10 +362,13 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     if (tid == 0) {
       if (stamp) job.timeline[1 + l * 4 + 0] = clock64();
       tc_fence_after();
-      const unsigned a_addr = s32(sm.a), w_addr = s32(sm.w[l & 1]);
-      for (int k = 0; k < K / 16; ++k)
-        umma(tmem, umma_desc(a_addr + k * 2 * CHUNK_A, CHUNK_A, 128), umma_desc(w_addr + k * 2 * CHUNK_W, CHUNK_W, 128),
-             k > 0 ? 1u : 0u);
+      // descriptors advance by two K-chunks per MMA: only the 14-bit start-address field changes
+      const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A, 128), bd = umma_desc(s32(sm.w[l & 1]), CHUNK_W, 128);
+      const int nk = K / 16;
+      umma(tmem, ad, bd, 0u);
+#pragma unroll
+      for (int k = 1; k < 8; ++k)
+        if (k < nk) umma(tmem, ad + (unsigned long long)(k * ((2 * CHUNK_A) >> 4)), bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)), 1u);
       umma_commit(&sm.mbar);
       if (stamp) job.timeline[1 + l * 4 + 1] = clock64();
       // the next layer's weights were requested two layers ago: absorb that wait while the MMAs run
