@@ -453,6 +453,53 @@ def net_case(name, mz, n_rows, seed, N=50, B=2, K=2):
     print(f"net_{name}: rows={n_rows} weights={out['weights'].size}")
 
 
+def vision_case(name, A=4, S=61, H=126, L=4, n_rows=6, seed=21):
+    """Vision (ResNet-v2) fixture: blob in the vision hand-off layout + the reference's own inference outputs
+    (muzero_model.py:802-909 with is_RGB) on committed inputs.  BatchNorm statistics / affine parameters are
+    randomised (an untrained model has mean 0 / var 1, which would not exercise the eval-mode fold)."""
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN_DIR), "..", "stochastic-muzero_b200"))
+    from stochastic_muzero_b200.weights import pack_vision_weights
+    _, ref_model = ref_shim.load()
+    torch.manual_seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mz = ref_model.Muzero(model_structure="vision_model", observation_space_dimensions=ref_shim.Box(0, 1, (98, 98, 3)),
+                              action_space_dimensions=ref_shim.Discrete(A), state_space_dimensions=S,
+                              hidden_layer_dimensions=H, number_of_hidden_layer=L, device="cpu", use_amp=False)
+    g = torch.Generator().manual_seed(seed)
+    for fn in ("representation", "dynamics", "afterstate_dynamics", "prediction", "afterstate_prediction"):
+        for m in getattr(mz, fn + "_function").modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                with torch.no_grad():
+                    m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                    m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                    m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                    m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+    blob, shape = pack_vision_weights(mz)
+    obs = torch.rand(n_rows, 3, 98, 98, generator=g).half().float()     # stored as float16, so make it exact
+    actions = torch.randint(0, A, (n_rows,), generator=g)
+    rows = {k: [] for k in ("repr_h", "pred_policy", "pred_value", "adyn_h", "apred_policy", "apred_value", "dyn_h",
+                            "dyn_reward", "dpred_policy", "dpred_value")}
+    with torch.no_grad():
+        for i in range(n_rows):
+            h = mz.representation_function_inference(obs[i:i + 1])
+            p, v = mz.prediction_function_inference(h)
+            ah = mz.afterstate_dynamics_function_inference(h, int(actions[i]))
+            ap, av = mz.afterstate_prediction_function_inference(ah)
+            r, dh = mz.dynamics_function_inference(ah, int(actions[i]))
+            dp, dv = mz.prediction_function_inference(dh)
+            for k, val in (("repr_h", h[0].numpy()), ("pred_policy", p[0]), ("pred_value", v), ("adyn_h", ah[0].numpy()),
+                           ("apred_policy", ap[0]), ("apred_value", av), ("dyn_h", dh[0].numpy()), ("dyn_reward", r),
+                           ("dpred_policy", dp[0]), ("dpred_value", dv)):
+                rows[k].append(np.asarray(val))
+    out = {k: np.stack(v).astype(np.float32) for k, v in rows.items()}
+    out.update(weights=blob, dims=np.array([A, S, H, L], np.int32), obs=obs.numpy().astype(np.float16),
+               actions=actions.numpy().astype(np.int32))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"vision_{name}.npz"), **out)
+    print(f"vision_{name}: rows={n_rows} weights={blob.size}")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
@@ -480,6 +527,8 @@ def main():
     net_case("mlp_l0", ref_shim.make_muzero(obs_dim=4, action_dim=2, state_dim=31, hidden_dim=64,
                                             n_hidden=0, seed=2), n_rows=8, seed=13, N=11, B=2)
     net_case("ckpt450", ref_shim.load_checkpoint(450), n_rows=24, seed=14, N=50, B=4)
+    vision_case("a4", A=4, S=61, H=126, L=4, n_rows=6, seed=21)
+    vision_case("small", A=3, S=21, H=40, L=1, n_rows=4, seed=22)
 
 
 if __name__ == "__main__":

@@ -171,3 +171,110 @@ def pack_weights(model) -> Tuple[np.ndarray, ModelShape]:
     if blob.size != total:
         raise ValueError(f"packed {blob.size} floats, layout expects {total} (one-hot width mismatch?)")
     return blob, shape
+
+
+# ----------------------------------------------------------------------------------------------------
+# vision (ResNet-v2) family — neural_network_vision_model.py, BASELINE config 5
+# ----------------------------------------------------------------------------------------------------
+VISION_HW = 7                       # hidden state [3, 7, 7]; the reference fixes the model input to 98x98x3
+VISION_FLAT = 3 * VISION_HW * VISION_HW
+
+
+@dataclasses.dataclass(frozen=True)
+class VisionShape:
+    action_dim: int
+    state_dim: int          # categorical support size S of value / reward heads
+    hidden_dim: int         # H of the MLP heads
+    num_hidden_layers: int  # L: residual blocks per trunk AND tied hidden layers per MLP head
+
+
+def vision_blob_layout(shape: VisionShape):
+    """Flat fp32 hand-off layout of the vision family.  Residual block (vision:41-79): bn[4, c] = gamma, beta,
+    running_mean, running_var; conv1[c,c,3,3] (used twice), conv3[c,c,3,3].  MLP head: in.w[H,147] in.b,
+    [mid.w[H,H] mid.b if L>0 — tied], out.w[n,H] out.b.  Trunk residual blocks exist only when L > 0."""
+    A, S, H, L = shape.action_dim, shape.state_dim, shape.hidden_dim, shape.num_hidden_layers
+    spec = []
+
+    def res(prefix, c):
+        spec.extend([(f"{prefix}.bn", (4, c)), (f"{prefix}.conv1", (c, c, 3, 3)), (f"{prefix}.conv3", (c, c, 3, 3))])
+
+    def mlp(prefix, n_out):
+        spec.extend([(f"{prefix}.in.w", (H, VISION_FLAT)), (f"{prefix}.in.b", (H,))])
+        if L > 0:
+            spec.extend([(f"{prefix}.mid.w", (H, H)), (f"{prefix}.mid.b", (H,))])
+        spec.extend([(f"{prefix}.out.w", (n_out, H)), (f"{prefix}.out.b", (n_out,))])
+
+    spec.append(("repr.conv_in", (1, 3, 3, 3)))
+    res("repr.res_in", 1)
+    spec.append(("repr.conv_out", (3, 1, 3, 3)))
+    res("repr.res_out", 3)
+    res("repr.res_last", 3)
+    for net in ("dyn", "adyn"):
+        spec.extend([(f"{net}.conv", (3, 4, 3, 3)), (f"{net}.bn", (4, 3))])
+        res(f"{net}.res", 3)
+        if net == "dyn":
+            spec.extend([("dyn.conv_reward.w", (3, 4)), ("dyn.conv_reward.b", (3,))])
+            mlp("dyn.reward", S)
+    for net in ("pred", "apred"):
+        res(f"{net}.res", 3)
+        spec.extend([(f"{net}.conv_value.w", (3, 3)), (f"{net}.conv_value.b", (3,))])
+        mlp(f"{net}.value", S)
+        spec.extend([(f"{net}.conv_policy.w", (3, 3)), (f"{net}.conv_policy.b", (3,))])
+        mlp(f"{net}.policy", A)
+    layout, off = {}, 0
+    for name, shp in spec:
+        layout[name] = (off, shp)
+        off += int(np.prod(shp))
+    return layout, off
+
+
+def pack_vision_weights(model):
+    """Walk the modules of a reference-style vision `Muzero` -> (blob, VisionShape).  With L == 0 the trunks
+    have no residual block; the layout keeps the slots (identity: gamma=1, var=1, zero convs are NOT an
+    identity for a v2 block, so L == 0 is rejected rather than faked)."""
+    import torch
+
+    def res_parts(rb):
+        sc = rb.sequential_container
+        bn, c1, c3 = sc[0], sc[2], sc[5]
+        assert sc[8] is c1, "conv_1 is expected to be shared between positions 1 and 3 of the block"
+        return [torch.stack([bn.weight, bn.bias, bn.running_mean, bn.running_var]), c1.weight, c3.weight]
+
+    def bn_parts(bn):
+        return [torch.stack([bn.weight, bn.bias, bn.running_mean, bn.running_var])]
+
+    def mlp_parts(seq, L):
+        lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        assert len(lin) == L + 2 and all(m is lin[1] for m in lin[1:1 + L])
+        out = [lin[0].weight, lin[0].bias]
+        if L > 0:
+            out += [lin[1].weight, lin[1].bias]
+        return out + [lin[-1].weight, lin[-1].bias]
+
+    rep = _unwrap(model.representation_function)
+    dyn, ady = _unwrap(model.dynamics_function), _unwrap(model.afterstate_dynamics_function)
+    pre, apr = _unwrap(model.prediction_function), _unwrap(model.afterstate_prediction_function)
+    mlp_v = pre.nn_value[2]
+    lin = [m for m in mlp_v if isinstance(m, torch.nn.Linear)]
+    L = len(lin) - 2
+    if L < 1:
+        raise ValueError("vision family with number_of_hidden_layer == 0 is not supported")
+    shape = VisionShape(action_dim=int(pre.nn_policy[2][-1].weight.shape[0]), state_dim=int(lin[-1].weight.shape[0]),
+                        hidden_dim=int(lin[0].weight.shape[0]), num_hidden_layers=L)
+    ds = rep.sequential_downsampler[0].sequential_container
+    parts = [ds[0].weight] + res_parts(ds[1]) + [ds[3].weight] + res_parts(ds[4]) + res_parts(rep.sequential_downsampler[1])
+    for net in (dyn, ady):
+        sc = net.sequential_container
+        parts += [sc[0].weight] + bn_parts(sc[1]) + res_parts(sc[3])
+        if net is dyn:
+            parts += [net.sequential_reward[0].weight.reshape(3, 4), net.sequential_reward[0].bias]
+            parts += mlp_parts(net.sequential_reward[2], L)
+    for net in (pre, apr):
+        parts += res_parts(net.resnet[0])
+        parts += [net.nn_value[0].weight.reshape(3, 3), net.nn_value[0].bias] + mlp_parts(net.nn_value[2], L)
+        parts += [net.nn_policy[0].weight.reshape(3, 3), net.nn_policy[0].bias] + mlp_parts(net.nn_policy[2], L)
+    blob = np.concatenate([p.detach().float().cpu().numpy().ravel() for p in parts]).astype(np.float32)
+    _, total = vision_blob_layout(shape)
+    if blob.size != total:
+        raise ValueError(f"packed {blob.size} floats, vision layout expects {total}")
+    return blob, shape

@@ -51,3 +51,13 @@ def assert_dump_equal(got, exp, what=""):
                 f"{what}: column {k} differs at {np.flatnonzero(g != e)[:5]}"
     gm, em = np.asarray(got["minmax"], np.float32), np.asarray(exp["minmax"], np.float32)
     assert np.array_equal(gm, em), f"{what}: minmax {gm} vs {em}"
+
+
+def vision_cases():
+    return sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "vision_*.npz")))
+
+
+def load_vision_case(name):
+    z = dict(np.load(os.path.join(GOLDEN_DIR, f"vision_{name}.npz")))
+    z["obs"] = z["obs"].astype(np.float32)
+    return z

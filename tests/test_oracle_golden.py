@@ -83,3 +83,33 @@ def test_readout_oracle_matches_reference_game_methods(name):
             assert np.array_equal(pol, z["readout_policy"][b, t_i])
             idx, sampled = RO.select_action(pol, T, z["readout_u"][b, t_i])
             assert sampled == bool(z["readout_sampled"][b, t_i]) and idx == z["readout_index"][b, t_i]
+
+
+# ---------------------------------------------------------------------------------------------------
+# vision (ResNet-v2) network oracle vs the reference's inference outputs (BASELINE config 5 family)
+# ---------------------------------------------------------------------------------------------------
+# scale_to_bound_action normalises over the 3 channels of each pixel: when they nearly coincide the
+# division amplifies fp32 summation-order noise, hence the looser bar on hidden states
+VISION_HIDDEN_ATOL = 2e-4
+
+
+@pytest.mark.parametrize("name", golden_io.vision_cases())
+def test_vision_oracle_matches_reference_inference(name):
+    from oracle import vision_oracle as VO
+    z = golden_io.load_vision_case(name)
+    A, S, H, L = [int(v) for v in z["dims"]]
+    net = VO.VisionOracle(z["weights"], A, S, H, L)
+    np.testing.assert_allclose(net.representation(z["obs"]), z["repr_h"], atol=VISION_HIDDEN_ATOL)
+    p, v = net.prediction(z["repr_h"])
+    np.testing.assert_allclose(p, z["pred_policy"], atol=5e-6)
+    np.testing.assert_allclose(v, z["pred_value"], atol=1e-5, rtol=5e-5)
+    np.testing.assert_allclose(net.afterstate_dynamics(z["repr_h"], z["actions"]), z["adyn_h"], atol=VISION_HIDDEN_ATOL)
+    ap, av = net.afterstate_prediction(z["adyn_h"])
+    np.testing.assert_allclose(ap, z["apred_policy"], atol=5e-6)
+    np.testing.assert_allclose(av, z["apred_value"], atol=1e-5, rtol=5e-5)
+    r, dh = net.dynamics(z["adyn_h"], z["actions"])
+    np.testing.assert_allclose(dh, z["dyn_h"], atol=VISION_HIDDEN_ATOL)
+    np.testing.assert_allclose(r, z["dyn_reward"], atol=1e-5, rtol=5e-5)
+    dp, dv = net.prediction(z["dyn_h"])
+    np.testing.assert_allclose(dp, z["dpred_policy"], atol=5e-6)
+    np.testing.assert_allclose(dv, z["dpred_value"], atol=1e-5, rtol=5e-5)
