@@ -40,7 +40,11 @@ enum {
 enum {
   SMZ_NET_EXTERNAL = 0, /* caller supplies policy/value/reward (tape replay, host-model callback)   */
   SMZ_NET_FP32 = 1,     /* fused fp32 CUDA-core MLP step (parity mode, 1e-5 vs the reference)       */
-  SMZ_NET_BF16 = 2      /* fused bf16 tcgen05/TMEM MLP step, fp32 accumulate (throughput mode)      */
+  SMZ_NET_BF16 = 2,     /* fused bf16 tcgen05/TMEM MLP step, fp32 accumulate (throughput mode)      */
+  SMZ_NET_VISION = 3    /* vision (ResNet-v2, neural_network_vision_model.py) family, fp32 CUDA cores:
+                         * obs_dim must be 3*98*98 (the reference fixes the model input, muzero_model.py:336),
+                         * hidden state 3x7x7, state_dim/hidden_dim/num_hidden_layers = S/H/L of the MLP
+                         * heads and residual trunks, chance_dim == action_dim                           */
 };
 
 /* where uniform draws come from */

@@ -13,6 +13,7 @@
 #include "../../include/smz.h"
 #include "smz_kernels.h"
 #include "smz_net_bf16.h"
+#include "smz_net_vision.h"
 
 static thread_local char g_err[512] = "";
 
@@ -39,6 +40,7 @@ struct smz_engine {
   float* img32_buf;
   float* blob_buf;
   SmzBf16Image* bf16;    // tcgen05 path state (null unless net_mode == SMZ_NET_BF16)
+  SmzVisionImage* vision;  // vision family state (null unless net_mode == SMZ_NET_VISION)
   double* pbc_dev;
   unsigned long long* seed_dev;
   signed char* sign_dev;
@@ -91,8 +93,11 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if (c.action_dim > SMZ_MAX_POLICY || c.chance_dim > SMZ_MAX_POLICY)
     return fail(SMZ_E_CAPACITY, "smz_create: policy width %d/%d exceeds %d (one lane per policy entry)",
                 c.action_dim, c.chance_dim, SMZ_MAX_POLICY);
-  if (c.net_mode < SMZ_NET_EXTERNAL || c.net_mode > SMZ_NET_BF16) return fail(SMZ_E_INVALID_ARG, "bad net_mode");
-  if (c.net_mode != SMZ_NET_EXTERNAL) {
+  if (c.net_mode < SMZ_NET_EXTERNAL || c.net_mode > SMZ_NET_VISION) return fail(SMZ_E_INVALID_ARG, "bad net_mode");
+  if (c.net_mode == SMZ_NET_VISION) {
+    if (c.obs_dim != 3 * 98 * 98) return fail(SMZ_E_INVALID_ARG, "smz_create: vision models take 3x98x98 observations (obs_dim %d)", c.obs_dim);
+    if (c.action_dim != c.chance_dim) return fail(SMZ_E_INVALID_ARG, "smz_create: vision family needs chance_dim == action_dim");
+  } else if (c.net_mode != SMZ_NET_EXTERNAL) {
     if (c.obs_dim < 1 || c.state_dim < 2 || c.hidden_dim < 1 || c.num_hidden_layers < 0)
       return fail(SMZ_E_INVALID_ARG, "smz_create: model shape out of range");
     if (c.hidden_dim > SMZ_HP || c.state_dim > SMZ_SP || c.obs_dim > SMZ_HP)
@@ -111,7 +116,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   e->cfg = c;
   memset(&e->dims, 0, sizeof(e->dims));
   memset(&e->a, 0, sizeof(e->a));
-  e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr;
+  e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr; e->vision = nullptr;
   e->n_trees = 0; e->sims_done = 0; e->have_weights = 0; e->launches = 0;
   e->use_pdl = getenv("SMZ_NO_PDL") ? 0 : 1;
   e->graph_exec = nullptr; e->graph_trees = e->graph_sims = e->graph_first = -1; e->capture_stream = nullptr;
@@ -123,7 +128,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   a.Kmax = a.Kd > a.Kc ? a.Kd : a.Kc;
   a.M = 1 + a.A + a.N * a.Kmax;
   a.W = a.A > a.C ? a.A : a.C;
-  a.Sp = SMZ_SP;
+  a.Sp = c.net_mode == SMZ_NET_VISION ? SMZ_VISION_SP : SMZ_SP;
   a.path_stride = a.N + 2;
   a.n_phases = 1;
   a.rng_mode = c.rng_mode;
@@ -133,7 +138,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   a.alpha = c.root_dirichlet_alpha;
 
   e->dims.nodes_per_tree = a.M; e->dims.max_children = a.Kmax; e->dims.policy_stride = a.W;
-  e->dims.hidden_stride = SMZ_SP; e->dims.hidden_slots = a.N + 1; e->dims.path_stride = a.path_stride;
+  e->dims.hidden_stride = a.Sp; e->dims.hidden_slots = a.N + 1; e->dims.path_stride = a.path_stride;
   e->dims.lanes_per_tree = lanes;
   e->cfg.lanes_per_tree = lanes;
 
@@ -153,7 +158,11 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(e->pbc_dev, (size_t)a.N + 2);
   ALLOC(e->seed_dev, 2);
   ALLOC(e->sign_dev, (size_t)a.N + 2);
-  if (c.net_mode != SMZ_NET_EXTERNAL) {
+  if (c.net_mode == SMZ_NET_VISION) {
+    ALLOC(a.hidden, (size_t)(a.N + 1) * B * a.Sp);
+    e->dims.weight_blob_floats = smz_vision_blob_floats(a.A, c.state_dim, c.hidden_dim, c.num_hidden_layers);
+    ALLOC(e->blob_buf, e->dims.weight_blob_floats);
+  } else if (c.net_mode != SMZ_NET_EXTERNAL) {
     SmzNetShape& sh = e->shape;
     sh.obs = c.obs_dim; sh.A = a.A; sh.C = a.C; sh.S = c.state_dim; sh.H = c.hidden_dim; sh.L = c.num_hidden_layers;
     sh.OH = a.W; sh.obs_pad = (c.obs_dim + 31) / 32 * 32;
@@ -177,10 +186,12 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
     if (cudaMemcpy(e->seed_dev, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SMZ_E_CUDA, "seed upload failed");
   }
   if (rc == SMZ_OK && a.hidden) {
-    cudaError_t m = cudaMemset(a.hidden, 0, (size_t)(a.N + 1) * B * SMZ_SP * sizeof(float));
+    cudaError_t m = cudaMemset(a.hidden, 0, (size_t)(a.N + 1) * B * a.Sp * sizeof(float));
     if (m != cudaSuccess) rc = fail(SMZ_E_CUDA, "memset: %s", cudaGetErrorString(m));
   }
   if (rc == SMZ_OK && c.net_mode == SMZ_NET_BF16) rc = smz_bf16_create(e->shape, a, &e->bf16, g_err, sizeof(g_err));
+  if (rc == SMZ_OK && c.net_mode == SMZ_NET_VISION)
+    rc = smz_vision_create(a.A, c.state_dim, c.hidden_dim, c.num_hidden_layers, &e->vision, g_err, sizeof(g_err));
   if (rc == SMZ_OK && cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = fail(SMZ_E_CUDA, "cudaStreamCreate failed");
   if (rc != SMZ_OK) { smz_destroy(e); return rc; }
@@ -194,6 +205,7 @@ int smz_destroy(smz_engine* e) {
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
   if (e->bf16) smz_bf16_destroy(e->bf16);
+  if (e->vision) smz_vision_destroy(e->vision);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return SMZ_OK;
@@ -243,6 +255,12 @@ int smz_set_weights(smz_engine* e, const float* blob, uint64_t n_floats, int32_t
   CU(cudaSetDevice(e->cfg.device));
   CU(cudaMemcpyAsync(e->blob_buf, blob, n_floats * sizeof(float),
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  if (e->vision) {
+    int rc = smz_vision_pack(e->vision, e->blob_buf, s, g_err, sizeof(g_err));
+    if (rc != SMZ_OK) return rc;
+    e->have_weights = 1;
+    return SMZ_OK;
+  }
   smz_net_f32_pack(e->shape, e->blob_buf, e->img32_buf, &e->img32, s);
   if (e->bf16) {
     int rc = smz_bf16_pack(e->bf16, e->shape, e->blob_buf, s, g_err, sizeof(g_err));
@@ -293,7 +311,8 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   if (e->cfg.num_simulations == 0) train = 0;   // mcts.py:215-216
   const float* policy = root_policy;
   if (obs) {
-    if (e->bf16) smz_bf16_root(e->bf16, a, e->shape, n_trees, obs, s);
+    if (e->vision) { smz_vision_root(e->vision, a, n_trees, obs, s); e->launches += 1; }
+    else if (e->bf16) smz_bf16_root(e->bf16, a, e->shape, n_trees, obs, s);
     else smz_net_f32_root(a, e->shape, e->img32, n_trees, obs, s);
     e->launches += 1;
     policy = a.out_policy;
@@ -332,7 +351,8 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32
 }
 
 static void enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false) {
-  if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, s);
+  if (e->vision) smz_vision_sim(e->vision, e->a, e->n_trees, sim, s);
+  else if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, s);
   else smz_net_f32_sim(e->a, e->shape, e->img32, e->n_trees, sim, s);
 }
 
@@ -425,6 +445,13 @@ int smz_net_eval(smz_engine* e, int32_t which, int32_t n_rows, const float* in, 
   if (which < 0 || which > 5 || n_rows < 1) return fail(SMZ_E_INVALID_ARG, "smz_net_eval: bad which / n_rows");
   if ((which == 2 || which == 4) && !idx) return fail(SMZ_E_INVALID_ARG, "smz_net_eval: idx_dev required");
   CU(cudaSetDevice(e->cfg.device));
+  if (e->vision) {
+    if (smz_vision_eval(e->vision, which, n_rows, in, idx, hidden_out, policy_out, value_out, reward_out, e->a.W,
+                        (cudaStream_t)stream) != SMZ_OK)
+      return fail(SMZ_E_INVALID_ARG, "smz_net_eval: the vision family has no stand-alone network %d", which);
+    CU(cudaGetLastError());
+    return SMZ_OK;
+  }
   if (e->bf16)
     smz_bf16_eval(e->bf16, e->shape, which, n_rows, in, idx, hidden_out, policy_out, value_out, reward_out, code_out,
                   e->a.W, (cudaStream_t)stream);
@@ -496,7 +523,7 @@ int smz_read_hidden(smz_engine* e, int32_t slot, float* out, void* stream) {
     CU(cudaGetLastError());
     return SMZ_OK;
   }
-  CU(cudaMemcpyAsync(out, e->a.hidden + (size_t)slot * e->a.B * SMZ_SP, (size_t)e->n_trees * SMZ_SP * sizeof(float),
+  CU(cudaMemcpyAsync(out, e->a.hidden + (size_t)slot * e->a.B * e->a.Sp, (size_t)e->n_trees * e->a.Sp * sizeof(float),
                      cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SMZ_OK;
 }

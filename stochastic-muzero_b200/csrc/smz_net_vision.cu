@@ -1,0 +1,584 @@
+// smz_net_vision.cu — network step of the vision (ResNet-v2) model family, fp32 CUDA cores (parity mode).
+//
+// Reference: neural_network_vision_model.py — Residual_block v2 with one shared BatchNorm2d and conv_1 used
+// twice (:41-79), Down_sample (:81-119), Representation (:122-158), Dynamics / Afterstate_dynamics
+// (:161-226, :373-430), Prediction / Afterstate_prediction (:229-296, :433-492), channel-wise
+// scale_to_bound_action (:495-503); muzero_model.py facade for RGB models: action as a constant plane
+// (a+1)/A (:511-522), softmax on the policy, inverse_transform_with_support on value / reward.
+// BatchNorm runs in eval mode and is folded at pack time into a per-channel scale / shift.
+//
+// Hidden state = [3,7,7] = 147 floats (arena rows of 160).  The 3-channel convolutions are CUDA-core work
+// (no tensor-core shape); per simulation one CTA pushes 32 leaves through trunk convs + the 147->H->..->S/A
+// MLP heads with activations in shared memory and the head weights streamed through a cp.async ring.
+// The representation (98x98x3 -> 3x7x7) runs once per move, one CTA per tree, all feature maps in smem.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/smz.h"
+#include "smz_net_vision.h"
+
+namespace {
+
+constexpr int R = 32;               // leaves per CTA
+constexpr int NT = 256;
+constexpr int HW = 7, PIX = 49, FLAT = 147;
+constexpr int VSP = SMZ_VISION_SP;  // 160: hidden row stride == padded K of the first MLP layer
+constexpr int LD = VSP + 4;         // activation row stride of the MLP stage
+constexpr int KC = 32;
+constexpr float BN_EPS = 1e-5f;
+
+struct VRes { const float *bn_s, *bn_t, *c1, *c3; };
+struct VMlp { const float *in_wt, *in_b, *mid_wt, *mid_b, *out_wt, *out_b; };
+struct VDyn { const float *conv, *bn_s, *bn_t; VRes res; const float *cr_w, *cr_b; VMlp reward; };
+struct VPred { VRes res; const float *cv_w, *cv_b; VMlp value; const float *cp_w, *cp_b; VMlp policy; };
+struct VRepr { const float* conv_in; VRes res_in; const float* conv_out; VRes res_out, res_last; };
+struct VNets { VRepr repr; VDyn dyn, adyn; VPred pred, apred; int A, S, H, L; };
+
+struct SmemSim {
+  float x[R][LD];                 // MLP ping
+  float y[R][LD];                 // MLP pong
+  float w[2][KC][SMZ_HP];         // weight ring
+  float in4[R][4 * PIX];          // trunk input: state + action plane
+  float f0[R][FLAT], f1[R][FLAT], f2[R][FLAT];   // feature maps
+  int tree[R], slot[R], act[R];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// out[r][c] = act( sum_k in[r][k] * Wt[k][c] + b[c] ), 32 rows x 128 columns, K a multiple of 32 (ReLU heads)
+__device__ void dense(const float* __restrict__ wt, int K, const float* __restrict__ bias, const float (*in)[LD],
+                      float (*out)[LD], bool relu, float (*wbuf)[KC][SMZ_HP]) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int nchunks = K / KC;
+  auto issue = [&](int c) {
+    const float* src = wt + (size_t)c * KC * SMZ_HP;
+    float* dst = &wbuf[c & 1][0][0];
+#pragma unroll
+    for (int i = 0; i < (KC * SMZ_HP / 4) / NT; ++i) {
+      const int e = (i * NT + tid) * 4;
+      cp_async16(dst + e, src + e);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const float(*w)[SMZ_HP] = wbuf[c & 1];
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&in[ty * 2][c * KC + kk]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&in[ty * 2 + 1][c * KC + kk]);
+      const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&w[kk + q][tx * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&w[kk + q][tx * 8 + 4]);
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] = fmaf(av0[q], bv[j], acc[0][j]);
+          acc[1][j] = fmaf(av1[q], bv[j], acc[1][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = tx * 8 + j;
+      const float v = acc[i][j] + bias[c];
+      out[ty * 2 + i][c] = relu ? fmaxf(v, 0.f) : v;
+    }
+  __syncthreads();
+}
+
+// MLP head (vision:188-199 etc.): Linear(147,H) ReLU, L x [tied Linear(H,H) ReLU], Linear(H,n).  Input rows in
+// `in` (columns 147..159 zero).  Returns the buffer holding the n output logits (columns [0,n)).
+__device__ float (*mlp_head(const VMlp& m, int L, float (*in)[LD], float (*other)[LD], float (*wbuf)[KC][SMZ_HP]))[LD] {
+  float(*cur)[LD] = in;
+  float(*nxt)[LD] = other;
+  dense(m.in_wt, VSP, m.in_b, cur, nxt, true, wbuf);
+  { auto t = cur; cur = nxt; nxt = t; }
+  for (int l = 0; l < L; ++l) {
+    dense(m.mid_wt, SMZ_HP, m.mid_b, cur, nxt, true, wbuf);
+    auto t = cur; cur = nxt; nxt = t;
+  }
+  dense(m.out_wt, SMZ_HP, m.out_b, cur, nxt, false, wbuf);
+  return nxt;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// inverse_transform_with_support (muzero_model.py:575-591), S <= 64 logits, one warp per row
+__device__ float support_scalar(const float* logits, int S) {
+  const int lane = threadIdx.x & 31;
+  const float v0 = lane < S ? logits[lane] : -INFINITY, v1 = lane + 32 < S ? logits[lane + 32] : -INFINITY;
+  const float m = warp_max(fmaxf(v0, v1));
+  const float e0 = lane < S ? expf(v0 - m) : 0.f, e1 = lane + 32 < S ? expf(v1 - m) : 0.f;
+  const float z = warp_sum(e0 + e1);
+  const int half = S / 2;
+  const float y = warp_sum((float)(lane - half) * (e0 / z) + (float)(lane + 32 - half) * (e1 / z));
+  const float inner = __fadd_rn(1.f, __fmul_rn(0.004f, __fadd_rn(__fadd_rn(fabsf(y), 1.f), 0.001f)));
+  const float t = __fdiv_rn(__fsub_rn(__fsqrt_rn(inner), 1.f), 0.002f);
+  const float mag = __fsub_rn(__fmul_rn(t, t), 1.f);
+  return y > 0.f ? mag : (y < 0.f ? -mag : 0.f);
+}
+__device__ void policy_softmax(const float* logits, int n, float* dst) {
+  const int lane = threadIdx.x & 31;
+  const float v = lane < n ? logits[lane] : -INFINITY;
+  const float m = warp_max(v);
+  const float e = lane < n ? expf(v - m) : 0.f;
+  const float z = warp_sum(e);
+  if (lane < n) dst[lane] = e / z;
+}
+
+// ---- generic direct convolution over maps held in shared memory ---------------------------------------------
+// out[n][co][y][x] = sum_{ci,ky,kx} act(in[n][ci][y*s+ky-1][x*s+kx-1]) * w[co][ci][ky][kx]   (zero padded)
+// with act(v) = relu(v * bn_s[ci] + bn_t[ci]) when bn_s != null (pre-activation of the v2 block), else v.
+// Optional residual add.  n_img images, strides in floats.
+__device__ void conv3x3(const float* in, int in_stride, int Ci, int Hi, int Wi, int stride, float* out, int out_stride,
+                        int Co, const float* __restrict__ w, const float* __restrict__ bn_s,
+                        const float* __restrict__ bn_t, const float* res, int res_stride, int n_img) {
+  const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+  const int per = Co * Ho * Wo;
+  for (int o = threadIdx.x; o < n_img * per; o += blockDim.x) {
+    const int n = o / per, rem = o - n * per;
+    const int co = rem / (Ho * Wo), p = rem - co * (Ho * Wo);
+    const int oy = p / Wo, ox = p - oy * Wo;
+    const float* src = in + (size_t)n * in_stride;
+    float acc = 0.f;
+    for (int ci = 0; ci < Ci; ++ci) {
+      const float s = bn_s ? __ldg(bn_s + ci) : 1.f, t = bn_s ? __ldg(bn_t + ci) : 0.f;
+      const float* wk = w + (co * Ci + ci) * 9;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * stride + ky - 1;
+        if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * stride + kx - 1;
+          if (ix < 0 || ix >= Wi) continue;
+          float v = src[(ci * Hi + iy) * Wi + ix];
+          if (bn_s) v = fmaxf(fmaf(v, s, t), 0.f);
+          acc = fmaf(v, __ldg(wk + ky * 3 + kx), acc);
+        }
+      }
+    }
+    if (res) acc += res[(size_t)n * res_stride + rem];
+    out[(size_t)n * out_stride + rem] = acc;
+  }
+  __syncthreads();
+}
+
+// Residual_block v2 (vision:41-79): x -> [bn relu conv1] -> [bn relu conv3] -> [bn relu conv1] -> + x.
+// x, t1, t2 are three distinct buffers of equal geometry; the result lands in t1.
+__device__ void resblock(const VRes& r, const float* x, float* t1, float* t2, int stride, int C, int H, int W, int n_img) {
+  conv3x3(x, stride, C, H, W, 1, t1, stride, C, r.c1, r.bn_s, r.bn_t, nullptr, 0, n_img);
+  conv3x3(t1, stride, C, H, W, 1, t2, stride, C, r.c3, r.bn_s, r.bn_t, nullptr, 0, n_img);
+  conv3x3(t2, stride, C, H, W, 1, t1, stride, C, r.c1, r.bn_s, r.bn_t, x, stride, n_img);
+}
+
+// 1x1 convolution with bias, Ci -> 3 channels, on 7x7 maps; output flattened [n][147] into an MLP input row (LD)
+__device__ void conv1x1_to_rows(const float* in, int in_stride, int Ci, const float* __restrict__ w,
+                                const float* __restrict__ b, float (*rows)[LD], int n_img) {
+  for (int o = threadIdx.x; o < n_img * VSP; o += blockDim.x) {
+    const int n = o / VSP, e = o - n * VSP;
+    float acc = 0.f;
+    if (e < FLAT) {
+      const int co = e / PIX, p = e - co * PIX;
+      acc = __ldg(b + co);
+      for (int ci = 0; ci < Ci; ++ci) acc = fmaf(in[(size_t)n * in_stride + ci * PIX + p], __ldg(w + co * Ci + ci), acc);
+    }
+    rows[n][e] = acc;     // columns 147..159 are the zero padding of K
+  }
+  __syncthreads();
+}
+
+// scale_to_bound_action over the CHANNEL dimension (vision:495-503): per pixel min/max of the 3 channels.
+// Optionally applies ReLU first (the trunk ends with an activation, vision:205).  In place.
+__device__ void scale_channels(float* f, int stride, bool relu_first, int n_img) {
+  for (int o = threadIdx.x; o < n_img * PIX; o += blockDim.x) {
+    const int n = o / PIX, p = o - n * PIX;
+    float* q = f + (size_t)n * stride + p;
+    float a = q[0], b = q[PIX], c = q[2 * PIX];
+    if (relu_first) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f); }
+    const float lo = fminf(a, fminf(b, c)), hi = fmaxf(a, fmaxf(b, c));
+    float sc = hi - lo;
+    if (sc < 1e-5f) sc += 1e-5f;
+    q[0] = (a - lo) / sc; q[PIX] = (b - lo) / sc; q[2 * PIX] = (c - lo) / sc;
+  }
+  __syncthreads();
+}
+
+struct VJob {
+  int mode;             // 0 simulation (compacted rows), 1 root prediction (trees in order), 2 stand-alone eval
+  int which;            // eval: 1 pred, 2 adyn, 3 apred, 4 dyn
+  int n_rows;
+  const float* in;      // eval: rows [n][160]
+  const int* idx;       // eval: action / code per row
+  float* hidden_dst;    // [index][160]
+  float* policy_dst; float* value_dst; float* reward_dst;
+  int pstride;
+};
+
+__global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob job, int sim) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemSim& sm = *reinterpret_cast<SmemSim*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tile = blockIdx.x, branch = 0, count = job.n_rows;
+  bool do_trunk = true, do_pred = true;
+  if (job.mode == 0) {
+    const int n0 = a.branch_count[sim * 2 + 0], n1 = a.branch_count[sim * 2 + 1];
+    const int t0 = (n0 + R - 1) / R, t1 = (n1 + R - 1) / R;
+    if (tile < t0) { branch = 0; count = n0; }
+    else if (tile < t0 + t1) { branch = 1; count = n1; tile -= t0; }
+    else return;
+  } else {
+    if (tile * R >= count) return;
+    if (job.mode == 1) { do_trunk = false; branch = 1; }              // root: Prediction on slot 0
+    else {
+      do_trunk = (job.which == 2 || job.which == 4);
+      do_pred = (job.which == 1 || job.which == 3);
+      branch = (job.which == 4 || job.which == 1) ? 1 : 0;
+    }
+  }
+  if (tid < R) {
+    const int row = tile * R + tid;
+    int tree = -1, slot = 0, act = 0;
+    if (row < count) {
+      if (job.mode == 0) { const int4 rec = a.rows4[(size_t)branch * a.B + row]; tree = rec.x; slot = rec.y; act = rec.z; }
+      else { tree = row; act = (job.mode == 2 && job.idx) ? job.idx[row] : 0; }
+    }
+    sm.tree[tid] = tree; sm.slot[tid] = slot; sm.act[tid] = act;
+  }
+  __syncthreads();
+  // ---- load the input state of every row -----------------------------------------------------------------
+  for (int e = tid; e < R * 4 * PIX; e += NT) {
+    const int r = e / (4 * PIX), c = e - r * (4 * PIX);
+    const int tree = sm.tree[r];
+    float v = 0.f;
+    if (tree >= 0) {
+      if (c < FLAT) {
+        const float* src = (job.mode == 2) ? job.in + (size_t)tree * VSP
+                                           : a.hidden + ((size_t)sm.slot[r] * a.B + tree) * VSP;
+        v = src[c];
+      } else {
+        v = ((float)sm.act[r] + 1.f) / (float)nets.A;       // muzero_model.py:511-522
+      }
+    }
+    sm.in4[r][c] = v;
+    if (c < FLAT) sm.f0[r][c] = v;
+  }
+  __syncthreads();
+  float* state = &sm.f0[0][0];        // where the (new) state lives: [R][147]
+  if (do_trunk) {
+    const VDyn& d = branch ? nets.dyn : nets.adyn;
+    // conv(4->3) + BN + ReLU (folded: BN scale/shift applied to the conv OUTPUT, then ReLU)
+    conv3x3(&sm.in4[0][0], 4 * PIX, 4, HW, HW, 1, &sm.f0[0][0], FLAT, 3, d.conv, nullptr, nullptr, nullptr, 0, R);
+    for (int e = tid; e < R * FLAT; e += NT) {
+      const int c = (e % FLAT) / PIX;
+      float* q = &sm.f0[0][0] + e;
+      *q = fmaxf(fmaf(*q, __ldg(d.bn_s + c), __ldg(d.bn_t + c)), 0.f);
+    }
+    __syncthreads();
+    float *x = &sm.f0[0][0], *t1 = &sm.f1[0][0], *t2 = &sm.f2[0][0];
+    for (int l = 0; l < nets.L; ++l) {
+      resblock(d.res, x, t1, t2, FLAT, 3, HW, HW, R);
+      float* t = x; x = t1; t1 = t;
+    }
+    scale_channels(x, FLAT, true, R);
+    state = x;
+    for (int e = tid; e < R * VSP; e += NT) {
+      const int r = e / VSP, c = e - r * VSP;
+      const int tree = sm.tree[r];
+      if (tree >= 0 && job.hidden_dst) job.hidden_dst[(size_t)tree * VSP + c] = c < FLAT ? state[r * FLAT + c] : 0.f;
+    }
+    if (branch && (job.mode == 0 || job.which == 4)) {
+      // reward head (vision:180, :207-215): conv1x1(4->3) on the INPUT x, flatten, MLP, categorical support
+      conv1x1_to_rows(&sm.in4[0][0], 4 * PIX, 4, d.cr_w, d.cr_b, sm.x, R);
+      float(*o)[LD] = mlp_head(d.reward, nets.L, sm.x, sm.y, sm.w);
+      for (int r = warp; r < R; r += NT / 32) {
+        const float rew = support_scalar(o[r], nets.S);
+        if (sm.tree[r] >= 0 && lane == 0 && job.reward_dst) job.reward_dst[sm.tree[r]] = rew;
+      }
+      __syncthreads();
+    }
+  }
+  if (do_pred) {
+    const VPred& p = branch ? nets.pred : nets.apred;
+    float* x = state;
+    float* t1 = (x == &sm.f0[0][0]) ? &sm.f1[0][0] : &sm.f0[0][0];
+    float* t2 = &sm.f2[0][0];
+    if (x == t2) t2 = &sm.f1[0][0];
+    for (int l = 0; l < nets.L; ++l) {
+      resblock(p.res, x, t1, t2, FLAT, 3, HW, HW, R);
+      float* t = x; x = t1; t1 = t;
+    }
+    conv1x1_to_rows(x, FLAT, 3, p.cv_w, p.cv_b, sm.x, R);
+    float(*ov)[LD] = mlp_head(p.value, nets.L, sm.x, sm.y, sm.w);
+    for (int r = warp; r < R; r += NT / 32) {
+      const float val = support_scalar(ov[r], nets.S);
+      if (sm.tree[r] >= 0 && lane == 0 && job.value_dst) job.value_dst[sm.tree[r]] = val;
+    }
+    __syncthreads();
+    conv1x1_to_rows(x, FLAT, 3, p.cp_w, p.cp_b, sm.x, R);
+    float(*op)[LD] = mlp_head(p.policy, nets.L, sm.x, sm.y, sm.w);
+    for (int r = warp; r < R; r += NT / 32)
+      if (sm.tree[r] >= 0 && job.policy_dst) policy_softmax(op[r], nets.A, job.policy_dst + (size_t)sm.tree[r] * job.pstride);
+  }
+}
+
+// ---- representation: [3,98,98] -> [3,7,7], one CTA per tree --------------------------------------------------
+constexpr int IMG = 98, H1 = 49, H2 = 25, H3 = 13;
+struct SmemRepr {
+  float a[3 * H2 * H2 > H1 * H1 ? 3 * H2 * H2 : H1 * H1];
+  float b[3 * H2 * H2 > H1 * H1 ? 3 * H2 * H2 : H1 * H1];
+  float c[3 * H2 * H2 > H1 * H1 ? 3 * H2 * H2 : H1 * H1];
+};
+
+__device__ void avgpool3s2(const float* in, int C, int Hi, float* out) {
+  const int Ho = (Hi - 1) / 2 + 1;
+  for (int o = threadIdx.x; o < C * Ho * Ho; o += blockDim.x) {
+    const int c = o / (Ho * Ho), p = o - c * Ho * Ho, oy = p / Ho, ox = p - oy * Ho;
+    float acc = 0.f;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = oy * 2 + ky - 1, ix = ox * 2 + kx - 1;
+        if (iy >= 0 && iy < Hi && ix >= 0 && ix < Hi) acc += in[(c * Hi + iy) * Hi + ix];
+      }
+    out[o] = acc / 9.f;      // count_include_pad = True
+  }
+  __syncthreads();
+}
+
+// first strided conv reads the observation straight from global memory
+__device__ void conv_in_s2(const float* __restrict__ obs, const float* __restrict__ w, float* out) {
+  for (int o = threadIdx.x; o < H1 * H1; o += blockDim.x) {
+    const int oy = o / H1, ox = o - oy * H1;
+    float acc = 0.f;
+    for (int ci = 0; ci < 3; ++ci)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 + ky - 1;
+        if (iy < 0 || iy >= IMG) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * 2 + kx - 1;
+          if (ix < 0 || ix >= IMG) continue;
+          acc = fmaf(obs[(ci * IMG + iy) * IMG + ix], __ldg(w + ci * 9 + ky * 3 + kx), acc);
+        }
+      }
+    out[o] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT) k_vision_repr(VNets nets, int n_trees, const float* __restrict__ obs, float* hidden_dst) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemRepr& sm = *reinterpret_cast<SmemRepr*>(smem_raw);
+  const int tree = blockIdx.x;
+  if (tree >= n_trees) return;
+  const VRepr& rp = nets.repr;
+  float *x = sm.a, *t1 = sm.b, *t2 = sm.c, *t;
+  conv_in_s2(obs + (size_t)tree * 3 * IMG * IMG, rp.conv_in, x);                     // [1,49,49]
+  for (int i = 0; i < 2; ++i) { resblock(rp.res_in, x, t1, t2, 0, 1, H1, H1, 1); t = x; x = t1; t1 = t; }
+  conv3x3(x, 0, 1, H1, H1, 2, t1, 0, 3, rp.conv_out, nullptr, nullptr, nullptr, 0, 1);  // [3,25,25]
+  t = x; x = t1; t1 = t;
+  for (int i = 0; i < 2; ++i) { resblock(rp.res_out, x, t1, t2, 0, 3, H2, H2, 1); t = x; x = t1; t1 = t; }
+  avgpool3s2(x, 3, H2, t1);                                                          // [3,13,13]
+  t = x; x = t1; t1 = t;
+  for (int i = 0; i < 3; ++i) { resblock(rp.res_out, x, t1, t2, 0, 3, H3, H3, 1); t = x; x = t1; t1 = t; }
+  avgpool3s2(x, 3, H3, t1);                                                          // [3,7,7]
+  t = x; x = t1; t1 = t;
+  resblock(rp.res_last, x, t1, t2, 0, 3, HW, HW, 1);
+  x = t1;
+  scale_channels(x, 0, false, 1);
+  for (int c = threadIdx.x; c < VSP; c += blockDim.x) hidden_dst[(size_t)tree * VSP + c] = c < FLAT ? x[c] : 0.f;
+}
+
+// ---- weight image -----------------------------------------------------------------------------------------
+__global__ void k_copy(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+// bn[4][c] = gamma, beta, mean, var  ->  scale[c], shift[c]
+__global__ void k_fold_bn(float* __restrict__ s, float* __restrict__ t, const float* __restrict__ bn, int c) {
+  const int i = threadIdx.x;
+  if (i >= c) return;
+  const float sc = bn[i] / sqrtf(bn[3 * c + i] + BN_EPS);
+  s[i] = sc;
+  t[i] = bn[c + i] - bn[2 * c + i] * sc;
+}
+// W[out][in] -> Wt[k][128] zero padded
+__global__ void k_pack_wt(float* __restrict__ dst, const float* __restrict__ src, int n_out, int n_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out * n_in) return;
+  const int o = i / n_in, k = i % n_in;
+  dst[(size_t)k * SMZ_HP + o] = src[(size_t)o * n_in + k];
+}
+
+}  // namespace
+
+struct SmzVisionImage {
+  VNets nets;
+  float* pool;
+  size_t pool_floats;
+  uint64_t blob_floats;
+};
+
+namespace {
+struct Builder {
+  const float* blob; float* pool; size_t boff = 0, poff = 0; cudaStream_t s; bool dry; int A, S, H, L;
+  float* take(size_t n) { float* p = pool + poff; poff += (n + 3) / 4 * 4; return p; }
+  const float* raw(size_t n) {       // copy n floats verbatim
+    float* d = take(n);
+    if (!dry) k_copy<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, blob + boff, (int)n);
+    boff += n;
+    return d;
+  }
+  void bn(int c, const float** sc, const float** sh) {
+    float *a = take(c), *b = take(c);
+    if (!dry) k_fold_bn<<<1, 32, 0, s>>>(a, b, blob + boff, c);
+    boff += 4 * (size_t)c;
+    *sc = a; *sh = b;
+  }
+  VRes res(int c) { VRes r; bn(c, &r.bn_s, &r.bn_t); r.c1 = raw((size_t)c * c * 9); r.c3 = raw((size_t)c * c * 9); return r; }
+  const float* wt(int n_out, int n_in, int k_pad) {
+    float* d = take((size_t)k_pad * SMZ_HP);
+    if (!dry) k_pack_wt<<<(n_out * n_in + 255) / 256, 256, 0, s>>>(d, blob + boff, n_out, n_in);
+    boff += (size_t)n_out * n_in;
+    return d;
+  }
+  const float* vec128(int n) {
+    float* d = take(SMZ_HP);
+    if (!dry) k_copy<<<1, 128, 0, s>>>(d, blob + boff, n);
+    boff += n;
+    return d;
+  }
+  VMlp mlp(int n_out) {
+    VMlp m{};
+    m.in_wt = wt(H, FLAT, VSP); m.in_b = vec128(H);
+    if (L > 0) { m.mid_wt = wt(H, H, SMZ_HP); m.mid_b = vec128(H); }
+    m.out_wt = wt(n_out, H, SMZ_HP); m.out_b = vec128(n_out);
+    return m;
+  }
+  VNets all() {
+    VNets n{};
+    n.A = A; n.S = S; n.H = H; n.L = L;
+    n.repr.conv_in = raw(27); n.repr.res_in = res(1); n.repr.conv_out = raw(27); n.repr.res_out = res(3); n.repr.res_last = res(3);
+    for (int i = 0; i < 2; ++i) {
+      VDyn& d = i ? n.adyn : n.dyn;
+      d.conv = raw(108); bn(3, &d.bn_s, &d.bn_t); d.res = res(3);
+      if (i == 0) { d.cr_w = raw(12); d.cr_b = raw(3); d.reward = mlp(S); }
+    }
+    for (int i = 0; i < 2; ++i) {
+      VPred& p = i ? n.apred : n.pred;
+      p.res = res(3);
+      p.cv_w = raw(9); p.cv_b = raw(3); p.value = mlp(S);
+      p.cp_w = raw(9); p.cp_b = raw(3); p.policy = mlp(A);
+    }
+    return n;
+  }
+};
+}  // namespace
+
+uint64_t smz_vision_blob_floats(int A, int S, int H, int L) {
+  Builder b{nullptr, nullptr, 0, 0, nullptr, true, A, S, H, L};
+  b.all();
+  return b.boff;
+}
+
+int smz_vision_create(int A, int S, int H, int L, SmzVisionImage** out, char* err, size_t err_len) {
+  if (H > SMZ_HP || S > SMZ_SP || A > 32 || L < 1 || L > 16) {
+    snprintf(err, err_len, "vision network: need H<=%d, S<=%d, A<=32, 1<=L<=16 (got %d, %d, %d, %d)", SMZ_HP, SMZ_SP, H, S, A, L);
+    return SMZ_E_CAPACITY;
+  }
+  SmzVisionImage* im = new SmzVisionImage();
+  memset(im, 0, sizeof(*im));
+  Builder b{nullptr, nullptr, 0, 0, nullptr, true, A, S, H, L};
+  b.all();
+  im->pool_floats = b.poff;
+  im->blob_floats = b.boff;
+  if (cudaMalloc(&im->pool, im->pool_floats * sizeof(float)) != cudaSuccess) {
+    snprintf(err, err_len, "vision network: cudaMalloc of the weight image failed");
+    delete im;
+    return SMZ_E_CUDA;
+  }
+  im->nets.A = A; im->nets.S = S; im->nets.H = H; im->nets.L = L;
+  cudaFuncSetAttribute((const void*)k_vision_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSim));
+  cudaFuncSetAttribute((const void*)k_vision_repr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRepr));
+  *out = im;
+  return SMZ_OK;
+}
+
+void smz_vision_destroy(SmzVisionImage* im) {
+  if (!im) return;
+  cudaFree(im->pool);
+  delete im;
+}
+
+int smz_vision_pack(SmzVisionImage* im, const float* blob_dev, cudaStream_t s, char* err, size_t err_len) {
+  if (cudaMemsetAsync(im->pool, 0, im->pool_floats * sizeof(float), s) != cudaSuccess) {
+    snprintf(err, err_len, "vision network: memset failed");
+    return SMZ_E_CUDA;
+  }
+  Builder b{blob_dev, im->pool, 0, 0, s, false, im->nets.A, im->nets.S, im->nets.H, im->nets.L};
+  im->nets = b.all();
+  if (cudaGetLastError() != cudaSuccess) {
+    snprintf(err, err_len, "vision network: weight packing launch failed");
+    return SMZ_E_CUDA;
+  }
+  return SMZ_OK;
+}
+
+void smz_vision_root(SmzVisionImage* im, const SmzArena& a, int n_trees, const float* obs, cudaStream_t s) {
+  k_vision_repr<<<n_trees, NT, sizeof(SmemRepr), s>>>(im->nets, n_trees, obs, a.hidden);
+  VJob job{};
+  job.mode = 1; job.n_rows = n_trees; job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
+  k_vision_step<<<(n_trees + R - 1) / R, NT, sizeof(SmemSim), s>>>(a, im->nets, job, 0);
+}
+
+void smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, cudaStream_t s) {
+  VJob job{};
+  job.mode = 0; job.n_rows = n_trees;
+  job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * VSP;
+  job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
+  k_vision_step<<<(n_trees + R - 1) / R + 1, NT, sizeof(SmemSim), s>>>(a, im->nets, job, sim);
+}
+
+int smz_vision_eval(SmzVisionImage* im, int which, int n_rows, const float* in, const int* idx, float* hidden_out,
+                    float* policy_out, float* value_out, float* reward_out, int policy_stride, cudaStream_t s) {
+  if (which == 0) {
+    k_vision_repr<<<n_rows, NT, sizeof(SmemRepr), s>>>(im->nets, n_rows, in, hidden_out);
+    return SMZ_OK;
+  }
+  if (which < 1 || which > 4) return SMZ_E_INVALID_ARG;
+  VJob job{};
+  job.mode = 2; job.which = which; job.n_rows = n_rows; job.in = in; job.idx = idx;
+  job.hidden_dst = hidden_out; job.policy_dst = policy_out; job.value_dst = value_out; job.reward_dst = reward_out;
+  job.pstride = policy_stride;
+  SmzArena dummy{};
+  k_vision_step<<<(n_rows + R - 1) / R, NT, sizeof(SmemSim), s>>>(dummy, im->nets, job, 0);
+  return SMZ_OK;
+}

@@ -12,11 +12,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import ModelShape
+from .weights import VISION_FLAT, ModelShape, VisionShape
 
 SEARCH_KEYS = ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha", "root_exploration_fraction",
                "num_simulations", "maxium_action_sample", "number_of_player", "custom_loop")
-_NET = {"external": _lib.NET_EXTERNAL, "fp32": _lib.NET_FP32, "bf16": _lib.NET_BF16}
+_NET = {"external": _lib.NET_EXTERNAL, "fp32": _lib.NET_FP32, "bf16": _lib.NET_BF16, "vision": _lib.NET_VISION}
 _RNG = {"philox": _lib.RNG_PHILOX, "tape": _lib.RNG_TAPE}
 
 
@@ -78,7 +78,12 @@ class SearchEngine:
         cfg.discount = float(search["discount"])
         cfg.root_dirichlet_alpha = float(search["root_dirichlet_alpha"])
         cfg.root_exploration_fraction = float(search["root_exploration_fraction"])
-        if net != "external":
+        if net == "vision":
+            if not isinstance(model_shape, VisionShape) or model_shape.action_dim != self.A or self.Cdim != self.A:
+                raise ValueError("the vision network needs a VisionShape with action_dim == chance_dim == A")
+            cfg.obs_dim, cfg.state_dim = 3 * 98 * 98, model_shape.state_dim
+            cfg.hidden_dim, cfg.num_hidden_layers = model_shape.hidden_dim, model_shape.num_hidden_layers
+        elif net != "external":
             if model_shape is None:
                 raise ValueError("model_shape is required for an internal network")
             if (model_shape.action_dim, model_shape.chance_dim) != (self.A, self.Cdim):
@@ -86,6 +91,8 @@ class SearchEngine:
             cfg.obs_dim, cfg.state_dim = model_shape.obs_dim, model_shape.state_dim
             cfg.hidden_dim, cfg.num_hidden_layers = model_shape.hidden_dim, model_shape.num_hidden_layers
         self.model_shape = model_shape
+        # floats of a hidden-state row that carry data (the rest of the arena row is padding)
+        self.hidden_width = VISION_FLAT if net == "vision" else (model_shape.state_dim if model_shape else 0)
         cfg.net_mode, cfg.rng_mode = _NET[net], _RNG[rng]
         cfg.lanes_per_tree = int(lanes_per_tree)
         cfg.record = int(record)
@@ -216,12 +223,13 @@ class SearchEngine:
         w = ["repr", "pred", "adyn", "apred", "dyn", "enc"].index(which)
         x = self._dev(x, torch.float32, "eval_in")
         n = x.shape[0]
+        x = x.reshape(n, -1)
         if w not in (0, 5) and x.shape[1] != self.dims.hidden_stride:
             xp = torch.zeros(n, self.dims.hidden_stride, dtype=torch.float32, device=x.device)
             xp[:, :x.shape[1]] = x
             x = xp
         idx_t = self._dev(idx, torch.int32, "eval_idx")
-        S = self.model_shape.state_dim
+        S = self.hidden_width
         hidden = self._new(n, self.dims.hidden_stride, dtype=torch.float32)
         policy = torch.zeros(n, self.dims.policy_stride, dtype=torch.float32, device=x.device)
         value, reward = self._new(n, dtype=torch.float32), self._new(n, dtype=torch.float32)
@@ -264,7 +272,7 @@ class SearchEngine:
     def read_hidden(self, slot):
         out = self._new(self.n_trees, self.dims.hidden_stride, dtype=torch.float32)
         self._check(self.lib.smz_read_hidden(self._h, int(slot), self._ptr(out), self._stream))
-        return out[:, :self.model_shape.state_dim]
+        return out[:, :self.hidden_width]
 
     def read_record(self):
         n, N, W, A = self.n_trees, self.N, self.dims.policy_stride, self.A

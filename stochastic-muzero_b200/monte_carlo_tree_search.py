@@ -23,7 +23,7 @@ import torch
 
 from . import batched_model
 from .engine import SearchEngine, _is_chance
-from .weights import PackedModel, pack_weights, shape_of, weights_version
+from .weights import (PackedModel, VisionShape, pack_vision_weights, pack_weights, shape_of, weights_version)
 
 
 class Node(object):
@@ -273,7 +273,7 @@ class Monte_carlo_tree_search():
     def _is_fusable(model):
         if isinstance(model, PackedModel):
             return True
-        return getattr(model, "model_structure", None) == "mlp_model" and all(
+        return getattr(model, "model_structure", None) in ("mlp_model", "vision_model") and all(
             hasattr(model, f"{n}_function") for n in ("representation", "prediction", "afterstate_prediction",
                                                       "afterstate_dynamics", "dynamics", "encoder"))
 
@@ -288,15 +288,32 @@ class Monte_carlo_tree_search():
         if not self._is_fusable(model):
             return self._run_batch_external(observations, model, train, root_to_play)
         self.model = model
-        shape = shape_of(model)
+        vision = getattr(model, "model_structure", None) == "vision_model"
         obs = observations if torch.is_tensor(observations) else torch.as_tensor(np.asarray(observations))
         obs = obs.reshape(obs.shape[0], -1)
-        eng, key = self._engine(self._net, obs.shape[0], shape.action_dim, shape.chance_dim, shape)
-        ver = weights_version(model)
-        if self._weights_seen.get(key) != ver:
-            blob, _ = pack_weights(model)
-            eng.set_weights(blob)
-            self._weights_seen[key] = ver
+        if vision:
+            # vision (ResNet-v2) family: fp32 CUDA-core network step, observations [B, 3, 98, 98]
+            if isinstance(model, PackedModel):
+                shape = model.shape
+            else:
+                shape = self._weights_seen.get(("vshape", id(model)))
+            ver = weights_version(model)
+            if shape is None or self._weights_seen.get(("vver", id(model))) != ver:
+                blob, shape = pack_vision_weights(model) if not isinstance(model, PackedModel) else (model.blob, model.shape)
+                self._weights_seen[("vshape", id(model))], self._weights_seen[("vblob", id(model))] = shape, blob
+                self._weights_seen[("vver", id(model))] = ver
+            eng, key = self._engine("vision", obs.shape[0], shape.action_dim, shape.action_dim, shape)
+            if self._weights_seen.get(key) != ver:
+                eng.set_weights(self._weights_seen[("vblob", id(model))])
+                self._weights_seen[key] = ver
+        else:
+            shape = shape_of(model)
+            eng, key = self._engine(self._net, obs.shape[0], shape.action_dim, shape.chance_dim, shape)
+            ver = weights_version(model)
+            if self._weights_seen.get(key) != ver:
+                blob, _ = pack_weights(model)
+                eng.set_weights(blob)
+                self._weights_seen[key] = ver
         eng.set_seed(self._next_seed())
         eng.root(obs=obs, root_to_play=root_to_play, train=train)
         eng.simulate(self.num_simulations)
@@ -335,7 +352,7 @@ class Monte_carlo_tree_search():
         to_play = self.cycle.global_step()
         if self._is_fusable(model):
             obs = observation if torch.is_tensor(observation) else torch.as_tensor(np.asarray(observation))
-            batch = self.run_batch(obs.reshape(1, -1), model, train,
+            batch = self.run_batch(obs.reshape(1, *obs.shape[1:]) if obs.dim() > 1 else obs.reshape(1, -1), model, train,
                                    root_to_play=torch.tensor([to_play], dtype=torch.int32))
             eng = batch._engine
             dump = eng.export_tree(0)

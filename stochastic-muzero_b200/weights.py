@@ -72,16 +72,19 @@ def random_blob(shape: ModelShape, seed: int = 0, std: float = 1.0 / 137.035999)
 
 
 class PackedModel:
-    """Weights already in hand-off form (blob + shape): accepted by ``run_batch`` / ``run`` wherever a
+    """Weights already in hand-off form (blob + shape; a ModelShape for the MLP family, a VisionShape for the
+    vision family): accepted by ``run_batch`` / ``run`` wherever a
     reference ``Muzero`` is.  ``bump()`` after replacing ``blob`` in place to make engines re-upload."""
     model_structure = "mlp_model"
 
     def __init__(self, blob, shape: ModelShape):
-        _, total = blob_layout(shape)
+        _, total = vision_blob_layout(shape) if isinstance(shape, VisionShape) else blob_layout(shape)
         blob = np.ascontiguousarray(blob, dtype=np.float32)
         if blob.size != total:
             raise ValueError(f"blob has {blob.size} floats, shape needs {total}")
         self.blob, self.shape, self.version = blob, shape, 0
+        if isinstance(shape, VisionShape):
+            self.model_structure = "vision_model"
 
     def bump(self):
         self.version += 1
@@ -121,6 +124,7 @@ def weights_version(model) -> tuple:
         mod = getattr(model, f"{name}_function")
         vers.append(id(mod))
         vers.extend((p.data_ptr(), p._version) for p in mod.parameters())
+        vers.extend((b.data_ptr(), b._version) for b in mod.buffers())      # BatchNorm running statistics
     return tuple(vers)
 
 

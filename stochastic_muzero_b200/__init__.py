@@ -8,4 +8,5 @@ __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.absp
 from .engine import SearchEngine, SmzError  # noqa: E402,F401
 from .monte_carlo_tree_search import (  # noqa: E402,F401
     BatchedRoots, MinMaxStats, Monte_carlo_tree_search, Node, Player_cycle)
-from .weights import ModelShape, PackedModel, blob_layout, pack_weights, random_blob  # noqa: E402,F401
+from .weights import (ModelShape, PackedModel, VisionShape, blob_layout, pack_vision_weights, pack_weights,
+                      random_blob, vision_blob_layout)  # noqa: E402,F401

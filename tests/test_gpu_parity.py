@@ -527,3 +527,76 @@ def test_run_batch_with_external_batched_backend_matches_fused_engine():
     np.testing.assert_allclose(ext.root_values[agree].cpu().numpy(), fused.root_values[agree].cpu().numpy(),
                                atol=1e-5, rtol=5e-5)
     assert ext.hidden_store.shape == (31, 200, dims[3])
+
+
+# ---------------------------------------------------------------------------------------------------
+# vision (ResNet-v2) family, BASELINE config 5: native fp32 network step
+# ---------------------------------------------------------------------------------------------------
+VISION_HIDDEN_ATOL = 2e-4     # channel-wise scale_to_bound amplifies fp32 noise where the 3 channels nearly coincide
+
+
+def _vision_engine(z, B, N=50, **kw):
+    from stochastic_muzero_b200 import SearchEngine, VisionShape
+    A, S, H, L = [int(v) for v in z["dims"]]
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=N, maxium_action_sample=kw.pop("K", 2),
+                  number_of_player=1, custom_loop=None)
+    eng = SearchEngine(search, A, A, max_trees=B, model_shape=VisionShape(A, S, H, L), net="vision", **kw)
+    eng.set_weights(z["weights"])
+    return eng
+
+
+@pytest.mark.parametrize("name", golden_io.vision_cases())
+def test_vision_network_step_matches_reference_inference(name):
+    z = golden_io.load_vision_case(name)
+    n = z["obs"].shape[0]
+    eng = _vision_engine(z, B=64)
+    flat = lambda x: x.reshape(n, -1)                                            # noqa: E731
+    h = eng.net_eval("repr", z["obs"])["hidden"].cpu().numpy()
+    np.testing.assert_allclose(h, flat(z["repr_h"]), atol=VISION_HIDDEN_ATOL)
+    o = eng.net_eval("pred", flat(z["repr_h"]))
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["pred_policy"], atol=1e-5)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["pred_value"], **SCALAR_TOL)
+    ah = eng.net_eval("adyn", flat(z["repr_h"]), z["actions"])["hidden"].cpu().numpy()
+    np.testing.assert_allclose(ah, flat(z["adyn_h"]), atol=VISION_HIDDEN_ATOL)
+    o = eng.net_eval("apred", flat(z["adyn_h"]))
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["apred_policy"], atol=1e-5)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["apred_value"], **SCALAR_TOL)
+    o = eng.net_eval("dyn", flat(z["adyn_h"]), z["actions"])
+    np.testing.assert_allclose(o["hidden"].cpu().numpy(), flat(z["dyn_h"]), atol=VISION_HIDDEN_ATOL)
+    np.testing.assert_allclose(o["reward"].cpu().numpy(), z["dyn_reward"], **SCALAR_TOL)
+    o = eng.net_eval("pred", flat(z["dyn_h"]))
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["dpred_policy"], atol=1e-5)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["dpred_value"], **SCALAR_TOL)
+    eng.close()
+
+
+def test_vision_full_search_config5_shape():
+    """BASELINE config 5 shape: vision model, A = 4, 1024 trees x 50 simulations on synthetic 98x98 RGB
+    observations; the engine's record replayed by the oracle, network outputs against the vision oracle."""
+    from oracle import vision_oracle as VO
+    z = golden_io.load_vision_case("a4")
+    A, S, H, L = [int(v) for v in z["dims"]]
+    B, N, seed = 1024, 50, 808
+    eng = _vision_engine(z, B=B, N=N, rng="philox", seed=seed, record=True)
+    obs = torch.rand(B, 3, 98, 98, generator=torch.Generator().manual_seed(4))
+    eng.root(obs=obs.reshape(B, -1), train=True)
+    eng.simulate(N)
+    eng.stats()
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    roots = eng.read_roots()
+    assert (roots["visits"].sum(1) == N).all()
+    cfg = O.SearchConfig(discount=0.997, num_simulations=N, maxium_action_sample=2)
+    for b in (0, 31, 32, 500, 1023):
+        model = O.TapeModel(rec["root_policy"][b, :A], rec["sim_policy"][b], np.full(N, A), rec["sim_value"][b],
+                            rec["sim_reward"][b])
+        tree = O.search(cfg, model, O.PhiloxUniforms(seed, b), train=True, dirichlet=rec["dirichlet"][b])
+        golden_io.assert_dump_equal(eng.export_tree(b), tree.dump(), f"vision[{b}]")
+    net = VO.VisionOracle(z["weights"], A, S, H, L)
+    sub = slice(0, 8)
+    h0 = net.representation(obs[sub].numpy())
+    np.testing.assert_allclose(eng.read_hidden(0)[sub].cpu().numpy(), h0.reshape(8, -1), atol=VISION_HIDDEN_ATOL)
+    pol, _ = net.prediction(h0)
+    np.testing.assert_allclose(rec["root_policy"][sub, :A], pol, atol=2e-5)
+    assert (rec["sim_branch"][:, 0] == 0).all()      # the first simulation always takes the afterstate pair
+    eng.close()
