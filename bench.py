@@ -25,6 +25,32 @@ SEARCH = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_al
 DIMS = dict(obs_dim=4, action_dim=2, chance_dim=2, state_dim=61, hidden_dim=126, num_hidden_layers=4)
 METRIC, UNIT = "mcts_simulations_per_sec", "sims/s"
 
+# BASELINE.json configs.  cfg2 is the bench line (the metric is quoted on it); the others are parity-test
+# shapes that can be timed on request (--workload) and are reported with the same JSON contract.
+WORKLOADS = {
+    "cfg2": dict(name="BASELINE configs[1]: CartPole MLP (obs 4, A 2, S 61, H 126, L 4)", trees=4096, sims=50,
+                 dims=DIMS, K=2, net=None),
+    "cfg3": dict(name="BASELINE configs[2]: stochastic 2048-like (4x4 board obs 16, 4 actions, 32 chance codes, K 32)",
+                 trees=8192, sims=100, dims=dict(DIMS, obs_dim=16, action_dim=4, chance_dim=32), K=32, net=None),
+    "cfg4": dict(name="BASELINE configs[3]: CartPole MLP, 65536 trees sharded across the ranks", trees=65536, sims=50,
+                 dims=DIMS, K=2, net=None, total=True),
+    "cfg5": dict(name="BASELINE configs[4]: vision ResNet-v2 (98x98 RGB, A 4, S 61, H 126, L 4)", trees=1024, sims=50,
+                 dims=dict(action_dim=4, state_dim=61, hidden_dim=126, num_hidden_layers=4), K=2, net="vision"),
+}
+
+
+def vision_flops_per_sim(d):
+    """2*MAC of the vision per-simulation networks: 3x3 convs on 3x7x7 maps + three 147->H->..->S/A MLP heads."""
+    H, L, S, A = d["hidden_dim"], d["num_hidden_layers"], d["state_dim"], d["action_dim"]
+    conv = lambda ci, co: 2 * ci * co * 9 * 49                                    # noqa: E731
+    res = 3 * conv(3, 3)
+    mlp = lambda n: 2 * (147 * H + L * H * H + H * n)                             # noqa: E731
+    trunk = conv(4, 3) + L * res
+    pred = L * res + 2 * 2 * 9 * 49 + mlp(S) + mlp(A)
+    after = trunk + pred
+    dyn = trunk + 2 * 12 * 49 + mlp(S) + pred
+    return after, dyn, 0
+
 
 def flops_per_sim(d):
     """2*MAC, trunk counted once, one-hot counted as dense S+A input."""
@@ -122,8 +148,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--net", default=os.environ.get("SMZ_BENCH_NET", "auto"), choices=["auto", "fp32", "bf16"])
-    ap.add_argument("--trees", type=int, default=4096, help="concurrent trees per GPU")
-    ap.add_argument("--sims", type=int, default=50)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--trees", type=int, default=None, help="concurrent trees per GPU (default: the workload's)")
+    ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--profile-only", action="store_true", help="timed steps only (for runs under ncu)")
@@ -135,8 +162,8 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from stochastic_muzero_b200 import (ModelShape, Monte_carlo_tree_search, PackedModel, SearchEngine,
-                                        random_blob)
+    from stochastic_muzero_b200 import (ModelShape, Monte_carlo_tree_search, PackedModel, SearchEngine, VisionShape,
+                                        random_blob, vision_blob_layout)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -147,17 +174,33 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    search = dict(SEARCH, num_simulations=args.sims)
-    shape = ModelShape(**DIMS)
-    B, N = args.trees, args.sims
-    net = args.net
+    wl = WORKLOADS[args.workload]
+    dims = wl["dims"]
+    N = args.sims or wl["sims"]
+    B = args.trees or (wl["trees"] // world if wl.get("total") else wl["trees"])
+    search = dict(SEARCH, num_simulations=N, maxium_action_sample=wl["K"])
+    vision = wl["net"] == "vision"
+    net = "vision" if vision else args.net
     if net == "auto":
         net = os.environ.get("SMZ_DEFAULT_NET", "bf16")
-    eng = SearchEngine(search, shape.action_dim, shape.chance_dim, max_trees=B, model_shape=shape, net=net,
+    shape = VisionShape(**dims) if vision else ModelShape(**dims)
+    A = shape.action_dim
+    C = A if vision else shape.chance_dim
+    obs_shape = (3 * 98 * 98,) if vision else (shape.obs_dim,)
+    eng = SearchEngine(search, A, C, max_trees=B, model_shape=shape, net=net,
                        rng="philox", seed=20240 + rank, tree_id_offset=rank * B, device=local)
 
     # weights: rank 0 draws them, one NCCL broadcast hands them to the other shards
-    blob = torch.from_numpy(random_blob(shape, seed=0)).to(dev) if rank == 0 else \
+    if vision:      # torch default init is not reproducible here: N(0, 0.05) convs / heads, identity-like BatchNorm
+        lay, tot = vision_blob_layout(shape)
+        w0 = (np.random.default_rng(0).standard_normal(tot) * 0.05).astype(np.float32)
+        for k, (o, shp) in lay.items():
+            if k.endswith(".bn"):
+                c = shp[1]
+                w0[o:o + 4 * c] = np.concatenate([np.ones(c), np.zeros(c), np.zeros(c), np.ones(c)])
+    else:
+        w0 = random_blob(shape, seed=0)
+    blob = torch.from_numpy(w0).to(dev) if rank == 0 else \
         torch.empty(eng.dims.weight_blob_floats, dtype=torch.float32, device=dev)
     bcast_ms = 0.0
     sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi takes a while to spin up
@@ -169,7 +212,13 @@ def main():
         torch.cuda.synchronize()
         bcast_ms = 1e3 * (time.perf_counter() - t0)
     eng.set_weights(blob)
-    obs = torch.randn(B, shape.obs_dim, generator=torch.Generator().manual_seed(rank)).to(dev)
+    gen = torch.Generator().manual_seed(rank)
+    if args.workload == "cfg3":      # 4x4 board, log2(tile)/16 with tiles drawn from {0..11}
+        obs = (torch.randint(0, 12, (B,) + obs_shape, generator=gen).float() / 16.0).to(dev)
+    elif vision:
+        obs = torch.rand((B,) + obs_shape, generator=gen).to(dev)
+    else:
+        obs = torch.randn((B,) + obs_shape, generator=gen).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step():
@@ -227,7 +276,7 @@ def main():
     t_sel = sum(m[0].elapsed_time(m[1]) for m in marks) / N
     t_net = sum(m[1].elapsed_time(m[2]) for m in marks) / N
     t_exp = sum(m[2].elapsed_time(m[3]) for m in marks) / N
-    f_after, f_dyn, f_root = flops_per_sim(DIMS)
+    f_after, f_dyn, f_root = vision_flops_per_sim(dims) if vision else flops_per_sim(dims)
     n_dyn = int(n_dyn.item())
     flops_launch = ((B * N - n_dyn) * f_after + n_dyn * f_dyn) / N
     peaks = {}
@@ -240,15 +289,24 @@ def main():
     which = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     achieved_tf = flops_launch / (t_net * 1e-3) / 1e12
     depth = stats["mean_leaf_depth"]
-    tb = tree_bytes_per_sim(depth, SEARCH["maxium_action_sample"], DIMS["state_dim"]) * B
+    tb = tree_bytes_per_sim(depth, min(wl["K"], max(A, C)), 147 if vision else dims["state_dim"]) * B
     achieved_gbs = tb / ((t_sel + t_exp) * 1e-3) / 1e9
-    roofline = {"kernel": "network step (%s)" % ("k_bf16_chain, tcgen05 bf16" if net == "bf16" else "k_net_sim, fp32 CUDA cores"), "bound": "tensor", "achieved": achieved_tf,
+    kname = {"bf16": "k_bf16_chain, tcgen05 bf16", "fp32": "k_net_sim, fp32 CUDA cores",
+             "vision": "k_vision_step, fp32 CUDA cores"}[net]
+    roofline = {"kernel": "network step (%s)" % kname, "bound": "tensor", "achieved": achieved_tf,
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
                 "peak_source": which + ", sustained bf16", "avg_launch_us": 1e3 * t_net,
                 "algorithmic_flops_per_launch": flops_launch,
                 "how": "CUDA events around each of the 50 launches of one extra search run step by step on the "
                        "launching stream after the timed region",
                 "share_of_step": N * t_net / (N * (t_sel + t_net + t_exp))}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.workload == "cfg2" and net in tr.get("network_step", {}):
+            roofline["traffic"] = tr["network_step"][net]
+            roofline["traffic_source"] = tr.get("source")
+    except Exception:
+        tr = {}
     roofline_tree = {"kernel": "k_select + k_expand_backup", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": which,
                      "avg_launch_us": {"select": 1e3 * t_sel, "expand_backup": 1e3 * t_exp},
@@ -257,7 +315,7 @@ def main():
     # ---- end to end through the public API: host observations in, host visit counts / values out -----
     mcts = Monte_carlo_tree_search(**{k: search[k] for k in search}, net=net, device=local, seed=77 + rank, max_batch=B)
     model = PackedModel(blob.cpu().numpy(), shape)
-    obs_host = torch.randn(B, shape.obs_dim).pin_memory()
+    obs_host = obs.cpu().pin_memory()
     for _ in range(3):
         r = mcts.run_batch(obs_host, model, train=True)
         r.visit_counts.cpu(); r.root_values.cpu()
@@ -288,10 +346,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32" if net == "fp32" else "bf16", "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[1]: CartPole MLP (obs 4, A 2, S 61, H 126, L 4) {B} "
-                                       f"concurrent trees x {N} simulations per GPU, synthetic N(0,1) observations, "
-                                       f"random-init weights N(0,1/137), device Philox RNG",
+                "vs_baseline": None, "dtype": "bf16" if net == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": f"{wl['name']}: {B} concurrent trees x {N} simulations per GPU, synthetic "
+                                       f"observations, random-init weights, device Philox RNG",
+                           "workload_id": args.workload,
                            "trees_per_gpu": B, "simulations": N, "network_step": net, "tree_arithmetic": "f32/f64 "
                            "(reference numpy semantics)", "l2": "256 MiB flush buffer written between timed steps",
                            "sharding": f"{world} x {B} independent trees, no data-path collective",
