@@ -193,6 +193,56 @@ __device__ void conv3x3(const float* in, int in_stride, int Ci, int Hi, int Wi, 
   __syncthreads();
 }
 
+// 3x3 convolution specialised for the per-simulation 7x7 maps: one thread per (leaf, pixel) produces all 3
+// output channels from a register-resident copy of the (at most 108) weights — the inner loop is pure FFMA
+// on shared-memory taps, no dependent global / constant loads.
+template <int CI, bool PRE>
+__device__ void conv7(const float* in, int in_stride, float* out, int out_stride, const float* __restrict__ wg,
+                      const float* __restrict__ bn_s, const float* __restrict__ bn_t, const float* res, int res_stride,
+                      int n_img) {
+  float w[3 * CI * 9];
+#pragma unroll
+  for (int i = 0; i < 3 * CI * 9; ++i) w[i] = __ldg(wg + i);
+  float s[CI], t[CI];
+#pragma unroll
+  for (int c = 0; c < CI; ++c) { s[c] = PRE ? __ldg(bn_s + c) : 1.f; t[c] = PRE ? __ldg(bn_t + c) : 0.f; }
+  for (int item = threadIdx.x; item < n_img * PIX; item += blockDim.x) {
+    const int n = item / PIX, p = item - n * PIX, y = p / HW, x = p - y * HW;
+    const float* src = in + (size_t)n * in_stride;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = y + ky - 1, ix = x + kx - 1;
+          float v = 0.f;
+          if (iy >= 0 && iy < HW && ix >= 0 && ix < HW) {
+            v = src[ci * PIX + iy * HW + ix];
+            if (PRE) v = fmaxf(fmaf(v, s[ci], t[ci]), 0.f);
+          }
+          acc0 = fmaf(v, w[(0 * CI + ci) * 9 + ky * 3 + kx], acc0);
+          acc1 = fmaf(v, w[(1 * CI + ci) * 9 + ky * 3 + kx], acc1);
+          acc2 = fmaf(v, w[(2 * CI + ci) * 9 + ky * 3 + kx], acc2);
+        }
+    if (res) {
+      const float* rr = res + (size_t)n * res_stride + p;
+      acc0 += rr[0]; acc1 += rr[PIX]; acc2 += rr[2 * PIX];
+    }
+    float* dst = out + (size_t)n * out_stride + p;
+    dst[0] = acc0; dst[PIX] = acc1; dst[2 * PIX] = acc2;
+  }
+  __syncthreads();
+}
+
+// the same residual block on batches of 7x7 maps (per-simulation networks)
+__device__ void resblock7(const VRes& r, const float* x, float* t1, float* t2, int n_img) {
+  conv7<3, true>(x, FLAT, t1, FLAT, r.c1, r.bn_s, r.bn_t, nullptr, 0, n_img);
+  conv7<3, true>(t1, FLAT, t2, FLAT, r.c3, r.bn_s, r.bn_t, nullptr, 0, n_img);
+  conv7<3, true>(t2, FLAT, t1, FLAT, r.c1, r.bn_s, r.bn_t, x, FLAT, n_img);
+}
+
 // Residual_block v2 (vision:41-79): x -> [bn relu conv1] -> [bn relu conv3] -> [bn relu conv1] -> + x.
 // x, t1, t2 are three distinct buffers of equal geometry; the result lands in t1.
 __device__ void resblock(const VRes& r, const float* x, float* t1, float* t2, int stride, int C, int H, int W, int n_img) {
@@ -248,7 +298,11 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemSim& sm = *reinterpret_cast<SmemSim*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int tile = blockIdx.x, branch = 0, count = job.n_rows;
+  // Three CTAs share a tile of 32 leaves, one per MLP head (the heads are ~80 % of the work and independent):
+  // head 0 = reward (dynamics pair only), 1 = value (also writes the new hidden state), 2 = policy.  The cheap
+  // convolution trunk is recomputed by each.
+  const int head = blockIdx.x % 3;
+  int tile = blockIdx.x / 3, branch = 0, count = job.n_rows;
   bool do_trunk = true, do_pred = true;
   if (job.mode == 0) {
     const int n0 = a.branch_count[sim * 2 + 0], n1 = a.branch_count[sim * 2 + 1];
@@ -265,6 +319,8 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
       branch = (job.which == 4 || job.which == 1) ? 1 : 0;
     }
   }
+  if (head == 0 && !(do_trunk && branch && (job.mode == 0 || job.which == 4))) return;   // no reward head here
+  if (head != 0 && !do_pred && !(head == 1 && do_trunk)) return;                            // nothing but a state write
   if (tid < R) {
     const int row = tile * R + tid;
     int tree = -1, slot = 0, act = 0;
@@ -297,7 +353,7 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
   if (do_trunk) {
     const VDyn& d = branch ? nets.dyn : nets.adyn;
     // conv(4->3) + BN + ReLU (folded: BN scale/shift applied to the conv OUTPUT, then ReLU)
-    conv3x3(&sm.in4[0][0], 4 * PIX, 4, HW, HW, 1, &sm.f0[0][0], FLAT, 3, d.conv, nullptr, nullptr, nullptr, 0, R);
+    conv7<4, false>(&sm.in4[0][0], 4 * PIX, &sm.f0[0][0], FLAT, d.conv, nullptr, nullptr, nullptr, 0, R);
     for (int e = tid; e < R * FLAT; e += NT) {
       const int c = (e % FLAT) / PIX;
       float* q = &sm.f0[0][0] + e;
@@ -306,7 +362,7 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
     __syncthreads();
     float *x = &sm.f0[0][0], *t1 = &sm.f1[0][0], *t2 = &sm.f2[0][0];
     for (int l = 0; l < nets.L; ++l) {
-      resblock(d.res, x, t1, t2, FLAT, 3, HW, HW, R);
+      resblock7(d.res, x, t1, t2, R);
       float* t = x; x = t1; t1 = t;
     }
     scale_channels(x, FLAT, true, R);
@@ -314,9 +370,9 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
     for (int e = tid; e < R * VSP; e += NT) {
       const int r = e / VSP, c = e - r * VSP;
       const int tree = sm.tree[r];
-      if (tree >= 0 && job.hidden_dst) job.hidden_dst[(size_t)tree * VSP + c] = c < FLAT ? state[r * FLAT + c] : 0.f;
+      if (head == 1 && tree >= 0 && job.hidden_dst) job.hidden_dst[(size_t)tree * VSP + c] = c < FLAT ? state[r * FLAT + c] : 0.f;
     }
-    if (branch && (job.mode == 0 || job.which == 4)) {
+    if (head == 0 && branch && (job.mode == 0 || job.which == 4)) {
       // reward head (vision:180, :207-215): conv1x1(4->3) on the INPUT x, flatten, MLP, categorical support
       conv1x1_to_rows(&sm.in4[0][0], 4 * PIX, 4, d.cr_w, d.cr_b, sm.x, R);
       float(*o)[LD] = mlp_head(d.reward, nets.L, sm.x, sm.y, sm.w);
@@ -327,27 +383,29 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
       __syncthreads();
     }
   }
-  if (do_pred) {
+  if (do_pred && head != 0) {
     const VPred& p = branch ? nets.pred : nets.apred;
     float* x = state;
     float* t1 = (x == &sm.f0[0][0]) ? &sm.f1[0][0] : &sm.f0[0][0];
     float* t2 = &sm.f2[0][0];
     if (x == t2) t2 = &sm.f1[0][0];
     for (int l = 0; l < nets.L; ++l) {
-      resblock(p.res, x, t1, t2, FLAT, 3, HW, HW, R);
+      resblock7(p.res, x, t1, t2, R);
       float* t = x; x = t1; t1 = t;
     }
-    conv1x1_to_rows(x, FLAT, 3, p.cv_w, p.cv_b, sm.x, R);
-    float(*ov)[LD] = mlp_head(p.value, nets.L, sm.x, sm.y, sm.w);
-    for (int r = warp; r < R; r += NT / 32) {
-      const float val = support_scalar(ov[r], nets.S);
-      if (sm.tree[r] >= 0 && lane == 0 && job.value_dst) job.value_dst[sm.tree[r]] = val;
+    if (head == 1) {
+      conv1x1_to_rows(x, FLAT, 3, p.cv_w, p.cv_b, sm.x, R);
+      float(*ov)[LD] = mlp_head(p.value, nets.L, sm.x, sm.y, sm.w);
+      for (int r = warp; r < R; r += NT / 32) {
+        const float val = support_scalar(ov[r], nets.S);
+        if (sm.tree[r] >= 0 && lane == 0 && job.value_dst) job.value_dst[sm.tree[r]] = val;
+      }
+    } else {
+      conv1x1_to_rows(x, FLAT, 3, p.cp_w, p.cp_b, sm.x, R);
+      float(*op)[LD] = mlp_head(p.policy, nets.L, sm.x, sm.y, sm.w);
+      for (int r = warp; r < R; r += NT / 32)
+        if (sm.tree[r] >= 0 && job.policy_dst) policy_softmax(op[r], nets.A, job.policy_dst + (size_t)sm.tree[r] * job.pstride);
     }
-    __syncthreads();
-    conv1x1_to_rows(x, FLAT, 3, p.cp_w, p.cp_b, sm.x, R);
-    float(*op)[LD] = mlp_head(p.policy, nets.L, sm.x, sm.y, sm.w);
-    for (int r = warp; r < R; r += NT / 32)
-      if (sm.tree[r] >= 0 && job.policy_dst) policy_softmax(op[r], nets.A, job.policy_dst + (size_t)sm.tree[r] * job.pstride);
   }
 }
 
@@ -556,7 +614,7 @@ void smz_vision_root(SmzVisionImage* im, const SmzArena& a, int n_trees, const f
   k_vision_repr<<<n_trees, NT, sizeof(SmemRepr), s>>>(im->nets, n_trees, obs, a.hidden);
   VJob job{};
   job.mode = 1; job.n_rows = n_trees; job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
-  k_vision_step<<<(n_trees + R - 1) / R, NT, sizeof(SmemSim), s>>>(a, im->nets, job, 0);
+  k_vision_step<<<3 * ((n_trees + R - 1) / R), NT, sizeof(SmemSim), s>>>(a, im->nets, job, 0);
 }
 
 void smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, cudaStream_t s) {
@@ -564,7 +622,7 @@ void smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim,
   job.mode = 0; job.n_rows = n_trees;
   job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * VSP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
-  k_vision_step<<<(n_trees + R - 1) / R + 1, NT, sizeof(SmemSim), s>>>(a, im->nets, job, sim);
+  k_vision_step<<<3 * ((n_trees + R - 1) / R + 1), NT, sizeof(SmemSim), s>>>(a, im->nets, job, sim);
 }
 
 int smz_vision_eval(SmzVisionImage* im, int which, int n_rows, const float* in, const int* idx, float* hidden_out,
@@ -579,6 +637,6 @@ int smz_vision_eval(SmzVisionImage* im, int which, int n_rows, const float* in, 
   job.hidden_dst = hidden_out; job.policy_dst = policy_out; job.value_dst = value_out; job.reward_dst = reward_out;
   job.pstride = policy_stride;
   SmzArena dummy{};
-  k_vision_step<<<(n_rows + R - 1) / R, NT, sizeof(SmemSim), s>>>(dummy, im->nets, job, 0);
+  k_vision_step<<<3 * ((n_rows + R - 1) / R), NT, sizeof(SmemSim), s>>>(dummy, im->nets, job, 0);
   return SMZ_OK;
 }
