@@ -53,7 +53,7 @@ struct smz_engine {
   cudaGraphExec_t graph_exec;
   int graph_trees, graph_sims, graph_first;
   cudaStream_t capture_stream;
-  int use_pdl;
+  int use_pdl, use_fused_tree;
 };
 
 const char* smz_last_error(void) { return g_err; }
@@ -119,6 +119,9 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr; e->vision = nullptr;
   e->n_trees = 0; e->sims_done = 0; e->have_weights = 0; e->launches = 0;
   e->use_pdl = getenv("SMZ_NO_PDL") ? 0 : 1;
+  // measured on B200 (4096 trees): the single-launch variant is ~4 % SLOWER than network kernel + tree kernel —
+  // 128 trees per SM on 33 SMs lose more to per-SM latency than the saved launch gains — so it is opt-in
+  e->use_fused_tree = getenv("SMZ_FUSED_TREE") ? 1 : 0;
   e->graph_exec = nullptr; e->graph_trees = e->graph_sims = e->graph_first = -1; e->capture_stream = nullptr;
 
   SmzArena& a = e->a;
@@ -148,7 +151,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.stat, B * M); ALLOC(a.link, B * M); ALLOC(a.root_prior, B * a.A); ALLOC(a.minmax, B);
   ALLOC(a.ucursor, B); ALLOC(a.root_to_play, B); ALLOC(a.path, B * a.path_stride); ALLOC(a.path_len, B);
   ALLOC(a.leaf_node, B); ALLOC(a.leaf_slot, B); ALLOC(a.leaf_action, B); ALLOC(a.leaf_branch, B);
-  ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 2 * B); ALLOC(a.rows4, 2 * B); ALLOC(a.error_flag, 1);
+  ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 4 * B); ALLOC(a.rows4, 4 * B); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
@@ -350,9 +353,9 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32
   return SMZ_OK;
 }
 
-static void enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false) {
+static void enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false, int tree_mode = 0) {
   if (e->vision) smz_vision_sim(e->vision, e->a, e->n_trees, sim, s);
-  else if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, s);
+  else if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, tree_mode, s);
   else smz_net_f32_sim(e->a, e->shape, e->img32, e->n_trees, sim, s);
 }
 
@@ -391,9 +394,14 @@ static void enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   // next kernel's CTAs become resident and run their prologue while the previous one drains.
   const bool pdl = e->bf16 != nullptr && e->use_pdl;
   smz_launch_select(a, G, e->n_trees, first, nullptr, nullptr, nullptr, s);
+  // tensor-core network + 4 lanes per tree: the tree phases run in the tail of the network kernel (one launch
+  // per simulation); otherwise a second, fused tree kernel follows each network step
+  const bool fuse = e->bf16 != nullptr && G == 4 && e->use_fused_tree;
   for (int sim = first; sim < first + n_sims; ++sim) {
+    const bool last = sim + 1 >= first + n_sims;
+    if (fuse) { enqueue_net(e, sim, s, pdl, last ? 1 : 2); continue; }
     enqueue_net(e, sim, s, pdl);
-    if (sim + 1 < first + n_sims) smz_launch_backup_select(a, G, e->n_trees, sim, pdl, s);
+    if (!last) smz_launch_backup_select(a, G, e->n_trees, sim, pdl, s);
     else smz_launch_expand_backup(a, G, e->n_trees, sim, a.out_policy, a.W, a.out_value, a.out_reward, s);
   }
 }
@@ -432,7 +440,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     e->graph_trees = e->n_trees; e->graph_sims = n_sims; e->graph_first = first;
   }
   CU(cudaGraphLaunch(e->graph_exec, s));
-  e->launches += 2LL * n_sims + 1;
+  e->launches += ((e->bf16 && e->cfg.lanes_per_tree == 4 && e->use_fused_tree) ? 1LL : 2LL) * n_sims + 1;
   e->sims_done += n_sims;
   return SMZ_OK;
 }

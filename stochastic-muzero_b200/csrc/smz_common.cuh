@@ -37,8 +37,10 @@ struct SmzArena {
   int* leaf_action; // [B] history[-1]
   int* leaf_branch; // [B]
   int* branch_count; // [N+1][2] rows per branch of each simulation
-  int* rows;        // [2][B] compacted tree ids per branch
-  int4* rows4;      // [2][B] same order: {tree, parent hidden slot, action, 0} — one load per gathered row
+  // compacted rows of a simulation, double-buffered by simulation parity (the descent of sim s+1 may run in
+  // the tail of the kernel that still gathers sim s in another CTA): index smz_row_index(a, sim, branch, row)
+  int* rows;        // [2 parities][2 branches][B] tree ids
+  int4* rows4;      // same order: {tree, parent hidden slot, action, 0} — one load per gathered row
   int* error_flag;  // [1]
   unsigned long long* depth_sum;  // [1] sum of leaf depths (bench bookkeeping)
   // network I/O
@@ -68,6 +70,9 @@ struct SmzArena {
 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ size_t smz_row_index(const SmzArena& a, int sim, int branch, int row) {
+  return (size_t)((sim & 1) * 2 + branch) * a.B + row;
+}
 // Programmatic dependent launch (PDL): `smz_pdl_wait` blocks until the preceding kernel of the stream has
 // completed and its writes are visible (no-op when the launch carries no programmatic dependency);
 // `smz_pdl_launch_dependents` lets the next kernel's CTAs become resident and run their prologue.

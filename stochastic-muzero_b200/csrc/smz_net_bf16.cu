@@ -23,6 +23,7 @@
 
 #include "../../include/smz.h"
 #include "smz_net_bf16.h"
+#include "smz_tree_dev.cuh"
 
 namespace {
 
@@ -81,6 +82,7 @@ struct Smem {
   unsigned long long bbar;
   unsigned int tmem_base;
   float4 part[4][TM];       // per-row partial reductions of the head epilogues, one slot per column block
+  int rowtree[TM];          // tree id of every row of the tile (-1 = none): the fused tree phase works on these
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -223,6 +225,10 @@ __device__ __forceinline__ float support_scalar(SoftPart a, SoftPart b) {
 // 32 accumulator columns 32*(w/4).. of every layer, so each SM sub-partition always has 4 warps to
 // interleave around the TMEM-load / MUFU latencies.
 // ---------------------------------------------------------------------------------------------
+// TREE = 0: network step only.  TREE = 1 / 2: the CTA also runs, for the 128 trees of its tile (4 lanes per
+// tree), the expansion + backup of simulation `sim` (1) and then the descent of simulation `sim + 1` (2) —
+// one launch per simulation instead of two, no second kernel ramp-up, outputs re-read from L1/L2.
+template <int TREE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
@@ -311,7 +317,7 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       int act = -1;
       if (valid) {
         if (job.input_kind == IN_GATHER) {
-          const int4 rec = a.rows4[(size_t)branch * a.B + row];     // {tree, parent slot, action, -}
+          const int4 rec = a.rows4[smz_row_index(a, sim, branch, row)];     // {tree, parent slot, action, -}
           index = rec.x;
           src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + index) * SMZ_SP;
           act = rec.z;
@@ -344,6 +350,7 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       }
     }
   }
+  if (cb == 0) sm.rowtree[r] = index;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -501,6 +508,21 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TN) : "memory");
   }
+  if constexpr (TREE > 0) {
+    // ---- tree phase for the trees of this tile: 4 lanes per tree, the policy / value / reward just written by
+    //      this CTA are visible after the barrier above ---------------------------------------------------------
+    using namespace smz_tree_dev;
+    Group<4> g;
+    int tree = sm.rowtree[tid >> 2];
+    const bool alive = tree >= 0;
+    if (!alive) tree = 0;
+    const SmzRng rng = smz_make_rng(a);
+    const TreeState ts = expand_backup_phase(g, a, rng, tree, alive, sim, a.out_policy, a.W, a.out_value, a.out_reward);
+    if constexpr (TREE > 1) {
+      __syncwarp();
+      select_phase(g, a, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -608,7 +630,9 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
     cudaMemset(im->timeline, 0, (1 + 4 * MAXL + 16) * sizeof(long long));
   }
-  cudaFuncSetAttribute((const void*)k_bf16_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_bf16_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_bf16_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_bf16_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
   *out = im;
   return SMZ_OK;
 }
@@ -722,18 +746,19 @@ void smz_bf16_root(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, i
   job.input_kind = IN_OBS; job.n_rows = n_trees; job.in = obs; job.obs = sh.obs; job.S = sh.S;
   job.hidden16_dst = reinterpret_cast<__nv_bfloat16*>(a.hidden);
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
-  k_bf16_chain<<<(n_trees + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
+  k_bf16_chain<0><<<(n_trees + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(a, im->chain_root, im->chain_root, job, 0);
 }
 
 void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, bool pdl,
-                  cudaStream_t s) {
+                  int tree_mode, cudaStream_t s) {
   Job job{};
   job.input_kind = IN_GATHER; job.n_rows = n_trees; job.S = sh.S;
   job.hidden16_dst = reinterpret_cast<__nv_bfloat16*>(a.hidden) + (size_t)(sim + 1) * a.B * SMZ_SP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   job.timeline = im->timeline;
-  smz_launch(k_bf16_chain, dim3(2 * ((n_trees + TM - 1) / TM)), dim3(NTHREADS), (size_t)im->smem_bytes, s, pdl, a,
-             im->chain_after, im->chain_dyn, job, sim);
+  const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
+  auto* k = tree_mode == 2 ? k_bf16_chain<2> : (tree_mode == 1 ? k_bf16_chain<1> : k_bf16_chain<0>);
+  smz_launch(k, grid, block, (size_t)im->smem_bytes, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
 }
 
 void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_rows, const float* in, const int* idx,
@@ -745,5 +770,5 @@ void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_row
   job.hidden_dst = hidden_out; job.policy_dst = policy_out; job.value_dst = value_out; job.reward_dst = reward_out;
   job.code_dst = code_out; job.pstride = policy_stride;
   SmzArena dummy{};
-  k_bf16_chain<<<(n_rows + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(dummy, im->chain_single[which], im->chain_single[which], job, 0);
+  k_bf16_chain<0><<<(n_rows + TM - 1) / TM, NTHREADS, im->smem_bytes, s>>>(dummy, im->chain_single[which], im->chain_single[which], job, 0);
 }

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(NT) k_net_sim(SmzArena a, SmzNetShape sh, SmzN
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid < R) {
     const int row = tile * R + tid;
-    const int tree = row < count ? a.rows[(size_t)branch * a.B + row] : -1;
+    const int tree = row < count ? a.rows[smz_row_index(a, sim, branch, row)] : -1;
     sm.tree[tid] = tree;
     sm.idx[tid] = tree >= 0 ? a.leaf_action[tree] : -1;
     sm.slot[tid] = tree >= 0 ? a.leaf_slot[tree] : 0;

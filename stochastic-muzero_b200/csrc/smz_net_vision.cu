@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
     const int row = tile * R + tid;
     int tree = -1, slot = 0, act = 0;
     if (row < count) {
-      if (job.mode == 0) { const int4 rec = a.rows4[(size_t)branch * a.B + row]; tree = rec.x; slot = rec.y; act = rec.z; }
+      if (job.mode == 0) { const int4 rec = a.rows4[smz_row_index(a, sim, branch, row)]; tree = rec.x; slot = rec.y; act = rec.z; }
       else { tree = row; act = (job.mode == 2 && job.idx) ? job.idx[row] : 0; }
     }
     sm.tree[tid] = tree; sm.slot[tid] = slot; sm.act[tid] = act;

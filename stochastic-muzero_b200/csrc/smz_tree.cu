@@ -12,116 +12,11 @@
 //   k_read_roots     game.py:179-204 consumer view (child visits, priors, rewards, root value)
 #include "smz_common.cuh"
 #include "smz_kernels.h"
+#include "smz_tree_dev.cuh"
 
 namespace {
 
-#define FULL 0xffffffffu
-
-// Every kernel below keeps all 32 lanes of a warp converged: loops run for the warp-wide maximum trip
-// count and per-group work is predicated, so every shuffle / ballot is a full-mask, constant-mask
-// instruction on sub-warp segments of width G (no mask matching, no dependence on independent
-// thread scheduling).  Trees beyond n_trees keep their lanes alive with `alive == false`.
-template <int G>
-struct Group {
-  int lane, gl, gbase;
-  __device__ Group() {
-    lane = threadIdx.x & 31;
-    gl = lane & (G - 1);
-    gbase = lane & ~(G - 1);
-  }
-  template <typename T>
-  __device__ T bcast(T v, int src) const { return __shfl_sync(FULL, v, src, G); }
-  __device__ unsigned ballot(bool p) const {
-    unsigned b = __ballot_sync(FULL, p);
-    return (G == 32) ? b : ((b >> gbase) & ((1u << G) - 1u));
-  }
-};
-
-// numpy float32 add.reduce over n values held one per lane (n may differ between the groups of a
-// warp): pairwise summation with an 8-way unrolled block (n >= 8) or a plain loop from 0.f (n < 8)
-// — numpy/_core/src/umath/loops_utils.h.src.  Trip counts are compile-time (G), adds are predicated.
-template <int G>
-__device__ float np_sum_f32(const Group<G>& g, float a, int n) {
-  float seq = 0.f;
-#pragma unroll
-  for (int i = 0; i < (G < 7 ? G : 7); ++i) {
-    const float v = g.bcast(a, i);
-    if (i < n) seq = __fadd_rn(seq, v);
-  }
-  if (G < 8) return seq;
-  float r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = g.bcast(a, j & (G - 1));
-  const int nb = n - (n % 8);
-#pragma unroll
-  for (int i = 8; i + 8 <= G; i += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v = g.bcast(a, (i + j) & (G - 1));
-      if (i < nb) r[j] = __fadd_rn(r[j], v);
-    }
-  }
-  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-#pragma unroll
-  for (int t = 0; t < 7; ++t) {
-    const float v = g.bcast(a, (nb + t) & (G - 1));
-    if (nb + t < n) res = __fadd_rn(res, v);
-  }
-  return n < 8 ? seq : res;
-}
-
-// cdf of RandomState.choice: float64 cumsum of p (sequential), divided by the last entry.
-// Every lane i < n returns cdf[i]; lanes >= n return 2.0 (never <= u).  Lanes >= n must pass p = 0.
-template <int G>
-__device__ double choice_cdf(const Group<G>& g, double p, int n) {
-  double acc = 0.0, mine = 0.0;
-#pragma unroll
-  for (int i = 0; i < G; ++i) {
-    acc = __dadd_rn(acc, g.bcast(p, i));     // + 0.0 beyond n leaves acc unchanged
-    if (g.gl == i) mine = acc;
-  }
-  return (g.gl < n) ? __ddiv_rn(mine, acc) : 2.0;
-}
-
-// (policy + 1e-12) / sum in float32 (mcts.py:205-206, :291-292); lanes >= n hold 0.
-template <int G>
-__device__ float normalise_policy(const Group<G>& g, float pol, int n) {
-  const float p = (g.gl < n) ? __fadd_rn(pol, 1e-12f) : 0.f;
-  const float s = np_sum_f32(g, p, n);
-  return (g.gl < n) ? __fdiv_rn(p, s) : 0.f;
-}
-
-// np.random.choice(n, bound, p=p, replace=False): returns the bit set of chosen indices and advances
-// the tree's uniform cursor by the number of draws numpy would have consumed.
-template <int G>
-__device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, const SmzRng& rng, bool alive, int tree,
-                                               float p32, int n, int bound, int& cursor) {
-  unsigned found = 0;
-  int nf = alive ? 0 : bound;
-  const double pd = (g.gl < n) ? (double)p32 : 0.0;
-  for (int round = 0; __any_sync(FULL, nf < bound); ++round) {
-    if (round > 2 * SMZ_MAX_POLICY) {   // NaN / degenerate policy: numpy would raise; do not hang
-      if (nf < bound) {
-        *a.error_flag = 2;
-        for (int i = 0; i < n && nf < bound; ++i)
-          if (!((found >> i) & 1u)) { found |= 1u << i; ++nf; }
-      }
-      break;
-    }
-    const int m = bound - nf;                    // 0 for groups that are done
-    const double c = choice_cdf(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n);
-    for (int j = 0; __any_sync(FULL, j < m); ++j) {
-      const bool on = j < m;
-      const double u = on ? smz_rng_uniform(rng, tree, cursor + j) : 0.0;
-      int idx = __popc(g.ballot(c <= u));
-      idx = idx < n ? idx : n - 1;
-      if (on && !((found >> idx) & 1u)) { found |= 1u << idx; ++nf; }
-    }
-    cursor += m;
-  }
-  return found;
-}
+using namespace smz_tree_dev;
 
 // ------------------------------------------------------------------------------------------------
 template <int G>
@@ -161,217 +56,6 @@ __global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__
     if (a.rec_root_policy)
       for (int i = 0; i < a.W; ++i) a.rec_root_policy[(size_t)tree * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Per-tree state that flows from the backup of one simulation into the descent of the next.  The fused
-// kernel keeps it in registers; the stand-alone kernels load / store it.
-struct TreeState {
-  int cursor;      // uniform draws consumed so far
-  float2 mm;       // MinMaxStats
-  int2 root;       // root {visit_count, value_sum bits}
-};
-
-// The search path is kept as one int4 record per level {node, visit_count, value_sum, reward} captured
-// while descending, so the backup needs ONE round trip (the record) instead of two (index -> stat).
-template <int G>
-__device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree, bool alive,
-                                             int sim, TreeState ts, int* __restrict__ o_slot, int* __restrict__ o_action,
-                                             int* __restrict__ o_branch) {
-  const size_t tb = (size_t)tree * a.M;
-  int cursor = ts.cursor;
-  const float vmin = ts.mm.x, vmax = ts.mm.y;
-  int4* path = a.path + (size_t)tree * a.path_stride;
-
-  int depth = 0, cbase = 1, nch = a.A;
-  int parent_visit = ts.root.x;
-  if (alive && g.gl == 0) path[0] = make_int4(0, ts.root.x, ts.root.y, 0);
-  int L = 1, child = 0, child_key = 0;
-  bool going = alive;
-  while (__any_sync(FULL, going)) {
-    const bool act = going && g.gl < nch;
-    const bool chance = (depth >> 1) & 1;
-    int4 st = make_int4(0, 0, 0, 0);
-    int2 lk = make_int2(0, 0);
-    double prior0 = 0.0, pbc = 0.0;
-    if (act) {
-      st = a.stat[tb + cbase + g.gl];
-      lk = a.link[tb + cbase + g.gl];
-      if (depth == 0) prior0 = a.root_prior[(size_t)tree * a.A + g.gl];
-      if (!chance) pbc = __ldg(a.pbc + parent_visit);
-    }
-    // the draw only depends on the cursor: it is computed while the loads are in flight
-    const double u = (going && (chance || act)) ? smz_rng_uniform(rng, tree, chance ? cursor : cursor + g.gl) : 0.0;
-    int pick = 0;
-    if (__any_sync(FULL, going && chance)) {
-      // chance node: sample a child from the smoothed priors (mcts.py:249-255, T9)
-      const float p = __int_as_float(st.w);
-      const float om = act ? __fadd_rn(__fsub_rn(1.f, p), 1e-12f) : 0.f;
-      const float rem = fabsf(__fdiv_rn(np_sum_f32(g, om, nch), (float)nch));
-      const float sh = act ? __fadd_rn(p, rem) : 0.f;
-      const float tot = np_sum_f32(g, sh, nch);
-      const float q = act ? __fdiv_rn(sh, tot) : 0.f;
-      const double c = choice_cdf(g, (double)q, nch);
-      int pk = __popc(g.ballot(act && c <= u));
-      pk = pk < nch ? pk : nch - 1;
-      if (chance) { pick = pk; cursor += going ? 1 : 0; }
-    }
-    if (__any_sync(FULL, going && !chance)) {
-      // decision node: argmax of ucb_score, one fresh uniform per child (mcts.py:235-243, T3/T5/T6)
-      double score = -__longlong_as_double(0x7ff0000000000000LL);
-      int best = -1;
-      if (act && !chance) {
-        const double prior = (depth == 0) ? prior0 : (double)__int_as_float(st.w);
-        // pbc = sqrt(n) * pb_c(n), the left-associated head of mcts.py:237, tabulated by the host
-        const double ps = __ddiv_rn(__dmul_rn(pbc, prior), (double)(st.x + 1));
-        double vs = 0.0;
-        if (st.x > 0) {
-          const float val = __fdiv_rn(__int_as_float(st.y), (float)st.x);
-          float v = __fadd_rn(__int_as_float(st.z), __fmul_rn(a.discount, val));
-          if (vmax > vmin) v = __fdiv_rn(__fsub_rn(v, vmin), __fsub_rn(vmax, vmin));
-          vs = (double)v;
-        }
-        const double noise = __dadd_rn(1e-7, __dmul_rn(2e-7 - 1e-7, u));
-        score = __dadd_rn(__dadd_rn(ps, vs), noise);
-        best = g.gl;
-      }
-#pragma unroll
-      for (int off = G / 2; off > 0; off >>= 1) {
-        const double os = __shfl_xor_sync(FULL, score, off, G);
-        const int ob = __shfl_xor_sync(FULL, best, off, G);
-        if (os > score || (os == score && ob > best)) { score = os; best = ob; }
-      }
-      if (!chance) { pick = best < 0 ? 0 : best; cursor += going ? nch : 0; }
-    }
-    const int4 cst = make_int4(g.bcast(st.x, pick), g.bcast(st.y, pick), g.bcast(st.z, pick), 0);
-    const int child_cb = g.bcast(lk.x, pick);
-    const int key = g.bcast(lk.y, pick);
-    if (going) {
-      child = cbase + pick;
-      child_key = key;
-      if (g.gl == 0) path[L] = make_int4(child, cst.x, cst.y, cst.z);
-      ++L;
-      if (child_cb == 0 || L >= a.path_stride) {
-        going = false;
-      } else {
-        // the child (depth+1) was expanded through the dynamics pair iff this node is a chance node (T2)
-        nch = chance ? a.Kd : a.Kc;
-        parent_visit = cst.x;
-        cbase = child_cb;
-        ++depth;
-      }
-    }
-  }
-  if (alive && g.gl == 0) {
-    const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
-    const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
-    a.leaf_node[tree] = child;
-    a.leaf_slot[tree] = slot;
-    a.leaf_action[tree] = child_key;
-    a.leaf_branch[tree] = branch;
-    a.path_len[tree] = L;
-    a.ucursor[tree] = cursor;
-    if (o_slot) o_slot[tree] = slot;
-    if (o_action) o_action[tree] = child_key;
-    if (o_branch) o_branch[tree] = branch;
-    const int r = atomicAdd(&a.branch_count[sim * 2 + branch], 1);
-    a.rows[(size_t)branch * a.B + r] = tree;
-    a.rows4[(size_t)branch * a.B + r] = make_int4(tree, slot, child_key, 0);
-    atomicAdd(a.depth_sum, (unsigned long long)(depth + 1));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree,
-                                                         bool alive, int sim, const float* __restrict__ policy,
-                                                         int pstride, const float* __restrict__ value,
-                                                         const float* __restrict__ reward) {
-  const size_t tb = (size_t)tree * a.M;
-  // everything this phase needs from memory is requested up front (one round trip): the leaf record,
-  // the network outputs, the tree state and — speculatively — the first two chunks of path records
-  const int4* path = a.path + (size_t)tree * a.path_stride;
-  const int4 rec0 = (g.gl < a.path_stride) ? path[g.gl] : make_int4(0, 0, 0, 0);
-  const int4 rec1 = (G + g.gl < a.path_stride) ? path[G + g.gl] : make_int4(0, 0, 0, 0);
-  const int leaf = a.leaf_node[tree];
-  const int branch = a.leaf_branch[tree];
-  const int L = alive ? a.path_len[tree] : 0;
-  int cursor = a.ucursor[tree];
-  float2 mm = a.minmax[tree];
-  float v = value[tree];
-  const float rew_in = reward[tree];
-  const signed char* sign = a.sign + (size_t)a.root_to_play[tree] * (a.N + 2);
-
-  // children of the leaf (mcts.py:289-297): width C after the afterstate pair, A after dynamics
-  const int n = branch ? a.A : a.C;
-  const int bound = min(a.K, n);
-  const float pol = (g.gl < n) ? policy[(size_t)tree * pstride + g.gl] : 0.f;
-  const float p = normalise_policy(g, pol, n);
-  const unsigned found = choice_without_replacement(g, a, rng, alive, tree, p, n, bound, cursor);
-  const int cb = 1 + a.A + sim * a.Kmax;
-  if (alive && g.gl < n && ((found >> g.gl) & 1u)) {
-    const int r = __popc(found & ((1u << g.gl) - 1u));
-    a.stat[tb + cb + r] = make_int4(0, 0, 0, __float_as_int(p));
-    a.link[tb + cb + r] = make_int2(0, g.gl);
-  }
-  const float rew = branch ? rew_in : 0.f;
-  if (alive && g.gl == 0) {
-    a.link[tb + leaf].x = cb;
-    a.ucursor[tree] = cursor;
-    if (branch) reinterpret_cast<int*>(a.stat + tb + leaf)[2] = __float_as_int(rew);     // Node.reward of the leaf
-    if (a.rec_policy) {
-      const size_t ro = ((size_t)tree * a.N + sim);
-      for (int i = 0; i < a.W; ++i) a.rec_policy[ro * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
-      a.rec_value[ro] = v;
-      a.rec_reward[ro] = rew;
-      a.rec_branch[ro] = (signed char)branch;
-    }
-  }
-
-  // backup leaf -> root (mcts.py:299-308): lanes own path levels, the discounted return is a serial
-  // float32 recurrence (mul then add, two roundings) carried through shuffles
-  int2 root = make_int2(0, 0);
-  int n_chunks = (L + G - 1) / G;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) n_chunks = max(n_chunks, __shfl_xor_sync(FULL, n_chunks, off));
-  for (int chunk = n_chunks - 1; chunk >= 0; --chunk) {
-    const int l = chunk * G + g.gl;
-    const bool valid = l < L;
-    int4 rec = chunk == 0 ? rec0 : rec1;
-    if (chunk > 1 && valid) rec = path[l];
-    if (!valid) rec = make_int4(0, 0, 0, 0);
-    if (valid && l == L - 1 && branch) rec.w = __float_as_int(rew);
-    const float r = __int_as_float(rec.w);
-    float myv = 0.f;
-#pragma unroll
-    for (int t = G - 1; t >= 0; --t) {
-      const float ri = g.bcast(r, t);
-      if (chunk * G + t < L) {
-        if (g.gl == t) myv = v;
-        v = __fadd_rn(ri, __fmul_rn(a.discount, v));
-      }
-    }
-    if (valid) {
-      const float vs = __fadd_rn(__int_as_float(rec.z), (signed char)__ldg(sign + l) > 0 ? myv : -myv);
-      const int2 upd = make_int2(rec.y + 1, __float_as_int(vs));
-      *reinterpret_cast<int2*>(a.stat + tb + rec.x) = upd;          // {visit_count, value_sum}
-      if (l == 0) root = upd;
-      const float nv = __fdiv_rn(vs, (float)upd.x);
-      mm.x = fminf(mm.x, nv);
-      mm.y = fmaxf(mm.y, nv);
-    }
-  }
-#pragma unroll
-  for (int off = G / 2; off > 0; off >>= 1) {
-    mm.x = fminf(mm.x, __shfl_xor_sync(FULL, mm.x, off, G));
-    mm.y = fmaxf(mm.y, __shfl_xor_sync(FULL, mm.y, off, G));
-  }
-  if (alive && g.gl == 0) a.minmax[tree] = mm;
-  TreeState ts;
-  ts.cursor = cursor;
-  ts.mm = mm;
-  ts.root = make_int2(g.bcast(root.x, 0), g.bcast(root.y, 0));   // level 0 lives in lane 0 of chunk 0
-  return ts;
 }
 
 template <int G>
