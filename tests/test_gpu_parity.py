@@ -600,3 +600,88 @@ def test_vision_full_search_config5_shape():
     np.testing.assert_allclose(rec["root_policy"][sub, :A], pol, atol=2e-5)
     assert (rec["sim_branch"][:, 0] == 0).all()      # the first simulation always takes the afterstate pair
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# randomised configurations: tapes produced by the (reference-pinned) oracle, replayed by the tree kernels
+# ---------------------------------------------------------------------------------------------------
+def _random_case(g, case_id):
+    A = int(g.integers(1, 33))
+    C = int(g.integers(1, 33))
+    K = int(g.integers(1, 34))
+    N = int(g.integers(0, 61))
+    players = int(g.integers(1, 4))
+    loop = None if g.random() < 0.8 else ">".join(str(int(v)) for v in g.integers(1, 4, int(g.integers(1, 5))))
+    cfg = dict(pb_c_base=int(g.integers(1, 30000)), pb_c_init=float(g.random() * 2), discount=float(0.8 + 0.2 * g.random()),
+               root_dirichlet_alpha=float(g.random()), root_exploration_fraction=float(g.random()),
+               num_simulations=N, maxium_action_sample=K, number_of_player=players, custom_loop=loop)
+    return cfg, A, C
+
+
+@pytest.mark.parametrize("case_id", range(12))
+def test_random_configurations_replay_oracle_tapes_bit_exact(case_id):
+    from stochastic_muzero_b200 import SearchEngine
+    g = np.random.default_rng(1000 + case_id)
+    cfg, A, C = _random_case(g, case_id)
+    N, B = cfg["num_simulations"], 6
+    ocfg = O.SearchConfig(**cfg)
+    n_phase = len(ocfg.cycle_map())
+    train = bool(g.random() < 0.7)
+    scale = float(10 ** g.uniform(-2, 1.5))
+    peaky = float(10 ** g.uniform(-1, 0.7))
+
+    class Stub:
+        def __init__(self, seed):
+            self.g = np.random.default_rng(seed)
+            self.rows = []
+
+        def _p(self, n):
+            z = self.g.normal(size=n) * peaky
+            e = np.exp(z - z.max())
+            return (e / e.sum()).astype(np.float32)
+
+        def root(self):
+            self.root_policy = self._p(A)
+            return None, self.root_policy, np.float32(0)
+
+        def afterstate(self, sim, h, a):
+            p, v = self._p(C), np.float32(self.g.normal() * scale)
+            self.rows.append((0, p, v, np.float32(0)))
+            return None, p, v
+
+        def dynamics(self, sim, h, a):
+            p, v, r = self._p(A), np.float32(self.g.normal() * scale), np.float32(self.g.normal() * scale)
+            self.rows.append((1, p, v, r))
+            return None, p, v, r
+
+    W = max(A, C)
+    trees, stubs, rngs, dirs, phases = [], [], [], [], []
+    for b in range(B):
+        stub, rng = Stub(case_id * 100 + b), O.MTUniforms(case_id * 100 + b)
+        d = np.random.default_rng(b).dirichlet([max(cfg["root_dirichlet_alpha"], 1e-3)] * A)
+        ph = int(g.integers(0, n_phase))
+        trees.append(O.search(ocfg, stub, rng, train=train, dirichlet=d, root_to_play=ph))
+        stubs.append(stub); rngs.append(rng); dirs.append(d); phases.append(ph)
+    U = max(len(r.log) for r in rngs) + 1
+    uni = np.zeros((B, U)); pol = np.zeros((B, max(N, 1), W), np.float32)
+    val = np.zeros((B, max(N, 1)), np.float32); rew = np.zeros((B, max(N, 1)), np.float32)
+    rootp = np.zeros((B, W), np.float32)
+    for b in range(B):
+        uni[b, :len(rngs[b].log)] = rngs[b].log
+        rootp[b, :A] = stubs[b].root_policy
+        for s, (br, p, v, r) in enumerate(stubs[b].rows):
+            pol[b, s, :len(p)], val[b, s], rew[b, s] = p, v, r
+    eng = SearchEngine(cfg, A, C, max_trees=B, net="external", rng="tape")
+    eng.set_uniform_tape(torch.from_numpy(uni))
+    eng.root(root_policy=torch.from_numpy(rootp), root_to_play=torch.tensor(phases, dtype=torch.int32), train=train,
+             dirichlet=torch.from_numpy(np.stack(dirs)))
+    pol_d, val_d, rew_d = (torch.from_numpy(x).cuda() for x in (pol, val, rew))
+    for s in range(N):
+        eng.select(s)
+        eng.expand_backup(s, pol_d[:, s].contiguous(), val_d[:, s].contiguous(), rew_d[:, s].contiguous())
+    eng.stats()
+    for b in range(B):
+        got = eng.export_tree(b)
+        golden_io.assert_dump_equal(got, trees[b].dump(), f"random[{case_id}][{b}] cfg={cfg} A={A} C={C}")
+        assert got["n_uniforms"] == len(rngs[b].log)
+    eng.close()
