@@ -339,6 +339,21 @@ def main():
            "ms_per_step": 1e3 * e2e_s / args.steps,
            "api": "Monte_carlo_tree_search.run_batch(pinned host observations) -> visit counts + root values on host"}
 
+    # ---- the reference's own call, one tree at a time (BASELINE configs[0] shape through the drop-in run()) ----
+    single = None
+    if rank == 0 and world == 1 and not vision:
+        one = Monte_carlo_tree_search(**{k: search[k] for k in search}, net="fp32", device=local, seed=5)
+        for _ in range(3):
+            one.run(observation=torch.randn(1, shape.obs_dim), model=model, train=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        moves = 20
+        for _ in range(moves):
+            root = one.run(observation=torch.randn(1, shape.obs_dim), model=model, train=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        single = {"ms_per_move": 1e3 * dt / moves, "value": moves * N / dt, "unit": UNIT,
+                  "api": "Monte_carlo_tree_search.run(observation, model, train) -> Node, fp32 network step, 1 tree"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
@@ -355,7 +370,7 @@ def main():
                            "sharding": f"{world} x {B} independent trees, no data-path collective",
                            "weight_broadcast_ms": bcast_ms},
                 "roofline": roofline, "roofline_tree": roofline_tree, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches, "clocks": clocks, "mean_leaf_depth": depth}
+                "gpu_launches": launches, "clocks": clocks, "mean_leaf_depth": depth, "single_tree_dropin": single}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

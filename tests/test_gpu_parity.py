@@ -685,3 +685,58 @@ def test_random_configurations_replay_oracle_tapes_bit_exact(case_id):
         golden_io.assert_dump_equal(got, trees[b].dump(), f"random[{case_id}][{b}] cfg={cfg} A={A} C={C}")
         assert got["n_uniforms"] == len(rngs[b].log)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# boundary behaviour: ragged batches, misuse errors (return codes of the C ABI surface as exceptions)
+# ---------------------------------------------------------------------------------------------------
+def test_partial_batch_equals_exact_size_engine():
+    zn = golden_io.load_net_case("mlp450_seed0")
+    obs = torch.randn(77, 4, generator=torch.Generator().manual_seed(9))
+    out = []
+    for cap in (77, 300):
+        for net in ("fp32", "bf16"):
+            e = _net_engine(zn, B=cap, N=20, net=net, rng="philox", seed=66)
+            e.root(obs=obs, train=True); e.simulate(20)
+            r = e.read_roots()
+            assert r["visits"].shape == (77, 2)
+            out.append((net, r["visits"].cpu().numpy(), r["root_values"].cpu().numpy()))
+            e.close()
+    for net in ("fp32", "bf16"):
+        a, b = [o for o in out if o[0] == net]
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), f"{net}: capacity changed the result"
+
+
+def test_api_misuse_is_reported_not_executed():
+    from stochastic_muzero_b200 import ModelShape, SearchEngine, SmzError
+    zn = golden_io.load_net_case("mlp_small")
+    obs_dim, A, C, S, H, L = [int(v) for v in zn["dims"]]
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=5, maxium_action_sample=2,
+                  number_of_player=1, custom_loop=None)
+    eng = SearchEngine(search, A, C, max_trees=8, model_shape=ModelShape(obs_dim, A, C, S, H, L), net="fp32")
+    with pytest.raises(SmzError, match="smz_set_weights has not been called"):
+        eng.root(obs=torch.zeros(4, obs_dim))
+    with pytest.raises(ValueError, match="blob has"):
+        eng.set_weights(np.zeros(10, np.float32))
+    eng.set_weights(zn["weights"])
+    with pytest.raises(SmzError, match="smz_root has not been called"):
+        eng.simulate(5)
+    with pytest.raises(ValueError, match="n_trees"):
+        eng.root(obs=torch.zeros(9, obs_dim))
+    eng.root(obs=torch.zeros(4, obs_dim), train=False)
+    with pytest.raises(ValueError, match="exceed num_simulations"):
+        eng.simulate(6)
+    eng.simulate(5)
+    with pytest.raises(ValueError, match="exceed num_simulations"):
+        eng.simulate(1)
+    with pytest.raises(ValueError, match="not in"):
+        eng.export_tree(4)
+    ext = SearchEngine(search, A, C, max_trees=8, net="external")
+    with pytest.raises(SmzError, match="has no network"):
+        ext.root(obs=torch.zeros(4, obs_dim))
+    with pytest.raises(SmzError, match="rng_mode is not TAPE"):
+        ext.set_uniform_tape(torch.zeros(8, 4, dtype=torch.float64))
+    with pytest.raises(ValueError, match="lanes_per_tree"):
+        SearchEngine(search, A, C, max_trees=8, net="external", lanes_per_tree=3)
+    eng.close(); ext.close()
