@@ -53,7 +53,7 @@ struct smz_engine {
   cudaGraphExec_t graph_exec;
   int graph_trees, graph_sims, graph_first;
   cudaStream_t capture_stream;
-  int use_pdl, use_fused_tree;
+  int use_pdl, use_fused_tree, use_mega;
 };
 
 const char* smz_last_error(void) { return g_err; }
@@ -119,6 +119,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr; e->vision = nullptr;
   e->n_trees = 0; e->sims_done = 0; e->have_weights = 0; e->launches = 0;
   e->use_pdl = getenv("SMZ_NO_PDL") ? 0 : 1;
+  e->use_mega = getenv("SMZ_MEGA") ? 1 : 0;
   // measured on B200 (4096 trees): the single-launch variant is ~4 % SLOWER than network kernel + tree kernel —
   // 128 trees per SM on 33 SMs lose more to per-SM latency than the saved launch gains — so it is opt-in
   e->use_fused_tree = getenv("SMZ_FUSED_TREE") ? 1 : 0;
@@ -153,6 +154,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.leaf_node, B); ALLOC(a.leaf_slot, B); ALLOC(a.leaf_action, B); ALLOC(a.leaf_branch, B);
   ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 4 * B); ALLOC(a.rows4, 4 * B); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
+  if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8); }
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
     ALLOC(a.rec_policy, B * a.N * a.W); ALLOC(a.rec_value, B * a.N); ALLOC(a.rec_reward, B * a.N);
@@ -205,6 +207,12 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
 int smz_destroy(smz_engine* e) {
   if (!e) return SMZ_OK;
   cudaSetDevice(e->cfg.device);
+  if (e->a.dbg) {
+    long long t[8];
+    if (cudaMemcpy(t, e->a.dbg, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "smz tree timeline (block 0, last fused launch): expand+backup %lld cycles | descent %lld cycles (path length of tree 0: %lld)\n",
+              t[1] - t[0], t[2] - t[1], t[3]);
+  }
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
   if (e->bf16) smz_bf16_destroy(e->bf16);
@@ -417,6 +425,14 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaSetDevice(e->cfg.device));
   const int first = e->sims_done;
+  if (e->use_mega && smz_bf16_mega_supported(e->bf16, e->a, e->cfg.lanes_per_tree)) {
+    // tensor-core network + narrow policies: one persistent launch runs the whole loop, tile by tile
+    smz_bf16_mega(e->bf16, e->a, e->shape, e->n_trees, first, n_sims, s);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    e->sims_done += n_sims;
+    return SMZ_OK;
+  }
   // The N-step loop is launch-bound: capture it once per (trees, first, count) into a CUDA graph and
   // replay it on the caller's stream.
   if (!e->graph_exec || e->graph_trees != e->n_trees || e->graph_sims != n_sims || e->graph_first != first) {

@@ -43,6 +43,7 @@ struct SmzArena {
   int4* rows4;      // same order: {tree, parent hidden slot, action, 0} — one load per gathered row
   int* error_flag;  // [1]
   unsigned long long* depth_sum;  // [1] sum of leaf depths (bench bookkeeping)
+  long long* dbg;   // debug clock stamps (null unless SMZ_TREE_TIMELINE is set)
   // network I/O
   float* out_policy;  // [B][W]
   float* out_value;   // [B]

@@ -526,6 +526,289 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The whole search loop of 128 trees in ONE persistent CTA (no inter-CTA dependency exists in the search:
+// trees are independent, so nothing but this tile's own progress gates the next simulation).
+// Per simulation: [expansion + backup of the previous one, descent of this one] on 4 lanes per tree ->
+// rows sorted by branch (afterstate leaves first) -> gather -> the 2(L+2)-layer chain with BOTH weight sets
+// resident per layer (afterstate-net tile and dynamics-net tile, accumulators in TMEM columns [0,128) and
+// [128,256)); each row's epilogue reads the accumulator half of its own branch.  No kernel boundary, no
+// per-launch prologue (TMEM, barriers, first weight tiles), no compaction atomics, no waiting for the deepest
+// tree of the whole batch.  Needs policy widths <= 4 (4 lanes per tree).
+// ---------------------------------------------------------------------------------------------
+struct SmemMega {
+  alignas(1024) unsigned char a[A_BYTES];
+  alignas(1024) unsigned char w[2][2][W_BYTES];   // [ring slot][0 = afterstate pair, 1 = dynamics pair]
+  float bias[2][MAXL][TN];
+  unsigned long long wbar[2];
+  unsigned long long mbar;
+  unsigned long long bbar;
+  unsigned int tmem_base;
+  float4 part[4][TM];
+  int rowtree[TM], rowslot[TM], rowact[TM];        // indexed by tile ROW (after the per-simulation sort)
+  int lslot[TM], lact[TM], lbranch[TM];            // indexed by LOCAL tree, written by the descent
+  int wcount[2][4];
+  int n_after;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_search_mega(SmzArena a, Chain chA, Chain chD, int n_trees, int first, int n_sims, int S, long long* timeline) {
+  using namespace smz_tree_dev;
+  extern __shared__ unsigned char smem_raw[];
+  SmemMega& sm = *reinterpret_cast<SmemMega*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = (warp & 3) * 32 + lane;   // chain role: row of the tile == TMEM lane
+  const int cb = warp >> 2;               // chain role: accumulator column block
+  const int c0 = cb * 32;
+  const int tile_base = blockIdx.x * TM;
+  const int nl = chA.n_layers, total = n_sims * nl;
+
+  auto load_weights = [&](int gl) {
+    const int l = gl % nl, slot = gl & 1;
+    const unsigned bytes = (unsigned)chA.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[slot], 2 * bytes);
+    bulk_g2s(sm.w[slot][0], chA.layer[l].w, bytes, &sm.wbar[slot]);
+    bulk_g2s(sm.w[slot][1], chD.layer[l].w, bytes, &sm.wbar[slot]);
+  };
+  if (tid == 0) {
+    mbar_init(&sm.wbar[0], 1);
+    mbar_init(&sm.wbar[1], 1);
+    mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.bbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bbytes = (unsigned)nl * TN * 4;
+    mbar_expect_tx(&sm.bbar, 2 * bbytes);
+    bulk_g2s(sm.bias[0], chA.bias, bbytes, &sm.bbar);
+    bulk_g2s(sm.bias[1], chD.bias, bbytes, &sm.bbar);
+    load_weights(0);
+    if (total > 1) load_weights(1);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(2 * TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---- tree role: 4 lanes per tree, the per-tree state stays in registers across the whole loop -----------
+  Group<4> g;
+  const int ltree = tid >> 2;
+  int tree = tile_base + ltree;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
+  const SmzRng rng = smz_make_rng(a);
+  TreeState ts;
+  ts.cursor = a.ucursor[tree];
+  ts.mm = a.minmax[tree];
+  { const int4 rs = a.stat[(size_t)tree * a.M]; ts.root = make_int2(rs.x, rs.y); }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = sm.tmem_base;
+  mbar_wait(&sm.bbar, 0);
+  if (tid == 0) mbar_wait(&sm.wbar[0], 0);
+
+  for (int it = 0; it < n_sims; ++it) {
+    const int sim = first + it;
+    const bool stamp = timeline && blockIdx.x == 0 && tid == 0 && it == n_sims - 1;
+    if (stamp) timeline[0] = clock64();
+    // ---- 1. tree phase -------------------------------------------------------------------------------------
+    if (it > 0) {
+      ts = expand_backup_phase(g, a, rng, tree, alive, sim - 1, a.out_policy, a.W, a.out_value, a.out_reward);
+      __syncwarp();
+    }
+    select_phase<4, false>(g, a, rng, tree, alive, sim, ts, sm.lslot - tile_base, sm.lact - tile_base, sm.lbranch - tile_base);
+    if (tid < TM) sm.rowtree[tid] = -1;
+    if (stamp) timeline[1 + 4 * MAXL + 0] = clock64();
+    __syncthreads();
+    if (stamp) timeline[1 + 4 * MAXL + 1] = clock64();
+    // ---- 2. sort the rows of the tile by branch: afterstate leaves first ---------------------------------------
+    unsigned m0 = 0, m1 = 0;
+    int mybranch = 2;
+    if (tid < TM) {
+      if (tile_base + tid < n_trees) mybranch = sm.lbranch[tid];
+      m0 = __ballot_sync(0xffffffffu, mybranch == 0);
+      m1 = __ballot_sync(0xffffffffu, mybranch == 1);
+      if (lane == 0) { sm.wcount[0][warp] = __popc(m0); sm.wcount[1][warp] = __popc(m1); }
+    }
+    __syncthreads();
+    if (tid < TM) {
+      int n0 = 0, pre0 = 0, pre1 = 0;
+      for (int w2 = 0; w2 < 4; ++w2) {
+        if (w2 < warp) { pre0 += sm.wcount[0][w2]; pre1 += sm.wcount[1][w2]; }
+        n0 += sm.wcount[0][w2];
+      }
+      const unsigned lt = (1u << lane) - 1u;
+      if (mybranch < 2) {
+        const int pos = mybranch == 0 ? pre0 + __popc(m0 & lt) : n0 + pre1 + __popc(m1 & lt);
+        sm.rowtree[pos] = tile_base + tid;
+        sm.rowslot[pos] = sm.lslot[tid];
+        sm.rowact[pos] = sm.lact[tid];
+      }
+      if (tid == 0) sm.n_after = n0;
+    }
+    __syncthreads();
+    // ---- 3. gather the parent hidden states (bf16 arena rows) + one-hot action into the A operand --------------
+    const int index = sm.rowtree[r];
+    const int n_after = sm.n_after;
+    const int br = r >= n_after;                     // this row's branch (rows beyond the last leaf: don't care)
+    {
+      const bool valid = index >= 0;
+      const __nv_bfloat16* src16 = valid
+          ? reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)sm.rowslot[r] * a.B + index) * SMZ_SP : nullptr;
+      const int act = valid ? sm.rowact[r] : -1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int kc = cb * 2 + q;
+        a_store(sm.a, r, kc, valid ? *reinterpret_cast<const uint4*>(src16 + kc * 8) : make_uint4(0, 0, 0, 0));
+      }
+      for (int kc = cb; kc < chA.onehot_pad / 8; kc += 4) {
+        unsigned w4[4] = {0, 0, 0, 0};
+        if (valid && act >= kc * 8 && act < kc * 8 + 8) {
+          const int j = act - kc * 8;
+          w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;
+        }
+        a_store(sm.a, r, 8 + kc, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (stamp) timeline[1 + 4 * MAXL + 2] = clock64();
+    // this warp's 32 rows all take the same branch unless the boundary falls inside them
+    const int q0 = (warp & 3) * 32;
+    const bool mixed = n_after > q0 && n_after < q0 + 32;
+    const unsigned taddr0 = tmem + ((unsigned)q0 << 16) + (unsigned)c0;
+
+    // ---- 4. the layer chain, both weight sets per layer -------------------------------------------------------
+    for (int l = 0; l < nl; ++l) {
+      const int gl = it * nl + l;
+      const int K = chA.layer[l].K;
+      const int kindA = chA.layer[l].kind;
+      if (tid == 0) {
+        if (stamp) timeline[1 + l * 4 + 0] = clock64();
+        tc_fence_after();
+        const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A, 128);
+        const int nk = K / 16;
+#pragma unroll
+        for (int net = 0; net < 2; ++net) {
+          const unsigned long long bd = umma_desc(s32(sm.w[gl & 1][net]), CHUNK_W, 128);
+          umma(tmem + net * TN, ad, bd, 0u);
+#pragma unroll
+          for (int k = 1; k < 8; ++k)
+            if (k < nk)
+              umma(tmem + net * TN, ad + (unsigned long long)(k * ((2 * CHUNK_A) >> 4)),
+                   bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)), 1u);
+        }
+        umma_commit(&sm.mbar);
+        if (stamp) timeline[1 + l * 4 + 1] = clock64();
+        if (gl + 1 < total) mbar_wait(&sm.wbar[(gl + 1) & 1], ((gl + 1) >> 1) & 1);
+      }
+      mbar_wait(&sm.mbar, gl & 1);
+      if (stamp) timeline[1 + l * 4 + 2] = clock64();
+      tc_fence_after();
+      if (tid == 0 && gl + 2 < total) load_weights(gl + 2);
+      const float* bias = sm.bias[br][l] + c0;
+
+      uint4 pend[4];
+      uint4* pend_dst = nullptr;
+      float x[32];
+      if (!mixed) {
+        tmem_ld32(taddr0 + (unsigned)(br * TN), x);
+      } else {
+        float y[32];
+        tmem_ld32(taddr0, x);
+        tmem_ld32(taddr0 + TN, y);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = br ? y[j] : x[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] += bias[j];
+
+      if (kindA == LK_HIDDEN) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = elu_fast(x[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          a_store(sm.a, r, cb * 4 + q,
+                  make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
+      } else {
+        // head layers: LK_STATE / LK_STATE_REWARD (end of the dynamics nets) or LK_PRED (end of the prediction nets)
+        const bool is_pred = kindA == LK_PRED;
+        const bool state_seg = !is_pred && cb < 2;
+        const bool soft_seg = (is_pred && cb < 2) || (!is_pred && br == 1 && cb >= 2);     // reward: dynamics rows only
+        SoftPart sp{-1e30f, 0.f, 0.f};
+        if (state_seg) {
+          float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { lo = fminf(lo, x[j]); hi = fmaxf(hi, x[j]); }
+          sm.part[cb][r] = make_float4(lo, hi, 0.f, 0.f);
+        } else if (soft_seg) {
+          sp = soft_part(x, c0 & 63, S);
+          sm.part[cb][r] = make_float4(sp.m, sp.z, sp.y, 0.f);
+        }
+        __syncthreads();
+        if (state_seg) {
+          const float4 o = sm.part[cb ^ 1][r];
+          const float lo = fminf(sm.part[cb][r].x, o.x), hi = fmaxf(sm.part[cb][r].y, o.y);
+          float scale = hi - lo;
+          if (scale < 1e-5f) scale += 1e-5f;
+          const float inv = 1.f / scale;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (x[j] - lo) * inv;
+          if (index >= 0)
+            pend_dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.hidden) +
+                                                ((size_t)(sim + 1) * a.B + index) * SMZ_SP + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            pend[q] = make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                 pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+            a_store(sm.a, r, cb * 4 + q, pend[q]);
+          }
+        } else if (soft_seg && (cb & 1) == 0) {
+          const float4 o = sm.part[cb + 1][r];
+          const float v = support_scalar(sp, SoftPart{o.x, o.y, o.z});
+          if (index >= 0) (is_pred ? a.out_value : a.out_reward)[index] = v;
+        } else if (is_pred && cb == 2) {
+          const int n = br ? chD.n_policy : chA.n_policy;
+          float m = -1e30f, z = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, x[i]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            x[i] = ex2f((x[i] - m) * 1.4426950408889634f);
+            z += x[i];
+          }
+          if (index >= 0) {
+            float* dst = a.out_policy + (size_t)index * a.W;
+            const float inv = 1.f / z;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < n) dst[i] = x[i] * inv;
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (pend_dst) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pend_dst[q] = pend[q];
+      }
+      if (stamp) timeline[1 + l * 4 + 3] = clock64();
+    }
+  }
+  // ---- expansion + backup of the last simulation ------------------------------------------------------------
+  expand_backup_phase(g, a, rng, tree, alive, first + n_sims - 1, a.out_policy, a.W, a.out_value, a.out_reward);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight image: torch Linear W[out][in] (fp32 blob) -> bf16 canonical B operand [K/8][128][8]
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_bf16(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int n_rows, int in_stride,
@@ -582,6 +865,7 @@ struct SmzBf16Image {
   size_t pool_bytes;
   int smem_bytes;
   long long* timeline;    // device debug buffer or null (SMZ_BF16_TIMELINE=1)
+  int timeline_mega;
 };
 
 static int round16(int v) { return (v + 15) / 16 * 16; }
@@ -648,6 +932,10 @@ void smz_bf16_destroy(SmzBf16Image* im) {
                 t[1 + l * 4] - t[0], t[1 + l * 4 + 1] - t[1 + l * 4], t[1 + l * 4 + 2] - t[1 + l * 4 + 1],
                 t[1 + l * 4 + 3] - t[1 + l * 4 + 2]);
       const long long* h = t + 1 + 4 * MAXL;
+      if (im->timeline_mega)
+        fprintf(stderr, "  persistent kernel, last simulation: tree phase %lld | barrier %lld | sort+gather %lld | to first layer +%lld\n",
+                h[0] - t[0], h[1] - h[0], h[2] - h[1], t[1] - h[2]);
+      else
       for (int k = 0; k < 2; ++k, h += 8)
         fprintf(stderr, "  %s head (thread 0): load+bias -> partials %lld | barrier %lld | finish %lld | fence+barrier %lld\n",
                 k ? "pred " : "state", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
@@ -759,6 +1047,24 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
   auto* k = tree_mode == 2 ? k_bf16_chain<2> : (tree_mode == 1 ? k_bf16_chain<1> : k_bf16_chain<0>);
   smz_launch(k, grid, block, (size_t)im->smem_bytes, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+}
+
+bool smz_bf16_mega_supported(const SmzBf16Image* im, const SmzArena& a, int lanes) {
+  return im != nullptr && lanes == 4 && a.A <= 4 && a.C <= 4 && im->chain_after.n_layers == im->chain_dyn.n_layers;
+}
+
+// the whole simulation loop [first, first + n_sims) as one persistent launch, one CTA per 128 trees
+void smz_bf16_mega(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int first, int n_sims,
+                   cudaStream_t s) {
+  const int smem = (int)sizeof(SmemMega) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute((const void*)k_search_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  k_search_mega<<<(n_trees + TM - 1) / TM, NTHREADS, smem, s>>>(a, im->chain_after, im->chain_dyn, n_trees, first, n_sims, sh.S,
+                                                                    im->timeline);
+  im->timeline_mega = 1;
 }
 
 void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_rows, const float* in, const int* idx,

@@ -22,3 +22,8 @@ void smz_bf16_eval(SmzBf16Image* im, const SmzNetShape& sh, int which, int n_row
                    int policy_stride, cudaStream_t s);
 // bf16 mode keeps the arena's hidden-state store in bf16 ([slot][B][64]); this widens one slot to fp32 rows
 void smz_bf16_read_hidden(const SmzArena& a, int slot, int n_trees, float* out, cudaStream_t s);
+// Persistent per-tile search kernel: the whole loop of simulations [first, first + n_sims) in one launch (needs
+// 4 lanes per tree, i.e. policy widths <= 4)
+bool smz_bf16_mega_supported(const SmzBf16Image* im, const SmzArena& a, int lanes);
+void smz_bf16_mega(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int first, int n_sims,
+                   cudaStream_t s);

@@ -96,10 +96,14 @@ __global__ void k_backup_select(SmzArena a, int n_trees, int sim) {
   int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool alive = tree < n_trees;
   if (!alive) tree = n_trees - 1;
+  const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) a.dbg[0] = clock64();
   const SmzRng rng = smz_make_rng(a);
   const TreeState ts = expand_backup_phase(g, a, rng, tree, alive, sim, a.out_policy, a.W, a.out_value, a.out_reward);
   __syncwarp();
+  if (stamp) a.dbg[1] = clock64();
   select_phase(g, a, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr);
+  if (stamp) { a.dbg[2] = clock64(); a.dbg[3] = a.path_len[tree]; }
 }
 
 // ------------------------------------------------------------------------------------------------
