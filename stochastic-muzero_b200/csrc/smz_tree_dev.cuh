@@ -126,7 +126,9 @@ struct TreeState {
 
 // The search path is kept as one int4 record per level {node, visit_count, value_sum, reward} captured
 // while descending, so the backup needs ONE round trip (the record) instead of two (index -> stat).
-template <int G>
+// COMPACT: append the tree to the per-branch row list of the simulation (one atomic per tree) for kernels that
+// re-tile the leaves by branch; the persistent per-tile kernel sorts its own rows instead.
+template <int G, bool COMPACT = true>
 __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree, bool alive,
                                              int sim, TreeState ts, int* __restrict__ o_slot, int* __restrict__ o_action,
                                              int* __restrict__ o_branch) {
@@ -226,9 +228,11 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     if (o_slot) o_slot[tree] = slot;
     if (o_action) o_action[tree] = child_key;
     if (o_branch) o_branch[tree] = branch;
-    const int r = atomicAdd(&a.branch_count[sim * 2 + branch], 1);
-    a.rows[smz_row_index(a, sim, branch, r)] = tree;
-    a.rows4[smz_row_index(a, sim, branch, r)] = make_int4(tree, slot, child_key, 0);
+    if (COMPACT) {
+      const int r = atomicAdd(&a.branch_count[sim * 2 + branch], 1);
+      a.rows[smz_row_index(a, sim, branch, r)] = tree;
+      a.rows4[smz_row_index(a, sim, branch, r)] = make_int4(tree, slot, child_key, 0);
+    }
     atomicAdd(a.depth_sum, (unsigned long long)(depth + 1));
   }
 }
