@@ -93,3 +93,20 @@ class SelfPlay:
             buf["rewards"][t], buf["dones"][t] = reward, done
             obs = env.reset(done)                                                   # finished games restart
         return buf
+
+
+@torch.no_grad()
+def reanalyse(mcts, model, observations: torch.Tensor, chunk: int = 16384, train: bool = True) -> Dict[str, torch.Tensor]:
+    """Reanalyse (self_play.py:30-44, game.py:112-116, replay_buffer.py:229-266): re-run the search over stored
+    observations of old games with the current weights.  Every stored position is an independent tree, so
+    the [T, B, ...] trajectory block is simply flattened into large batches for the engine.
+    Returns fresh targets: child_visits [T, B, A] (stored visit policy) and root_values [T, B]."""
+    T, B = observations.shape[:2]
+    flat = observations.reshape((T * B,) + tuple(observations.shape[2:]))
+    visits, values = [], []
+    for lo in range(0, T * B, chunk):
+        roots = mcts.run_batch(flat[lo:lo + chunk], model, train=train)
+        visits.append(roots.select_actions(0.0)["stored_policy"])
+        values.append(roots.root_values.clone())
+    child_visits = torch.cat(visits)
+    return {"child_visits": child_visits.reshape(T, B, -1), "root_values": torch.cat(values).reshape(T, B)}

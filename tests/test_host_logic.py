@@ -129,3 +129,63 @@ def test_philox_known_answer():
     assert O.philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
     assert O.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the oracle's restatements of numpy's legacy RandomState algorithms, checked against numpy itself
+# ---------------------------------------------------------------------------------------------------
+def test_choice_restatement_matches_numpy_randomstate():
+    """np.random.choice(n, size, p, replace=False) and choice(a, p=p): same picks AND same number of
+    underlying random_sample() draws as numpy's own implementation, for random p / n / size."""
+    g = np.random.default_rng(7)
+    for trial in range(300):
+        n = int(g.integers(1, 40))
+        size = int(g.integers(1, n + 1))
+        p = g.random(n).astype(np.float32) ** float(g.uniform(0.5, 6))
+        p = O.normalise_policy(p)
+        seed = int(g.integers(0, 2 ** 31))
+        ref = np.random.RandomState(seed)
+        expect = ref.choice(n, size, p=p, replace=False)
+        rng = O.MTUniforms(seed)
+        got = O.choice_without_replacement(n, size, p, rng)
+        assert list(expect) == got, f"trial {trial}: n={n} size={size}"
+        assert rng.rs.random_sample() == ref.random_sample(), "stream positions diverged (different draw count)"
+        # with replacement, size=None (select_child's chance branch)
+        ref2, rng2 = np.random.RandomState(seed), O.MTUniforms(seed)
+        q = O.smoothed_chance_probs(p)
+        e2 = ref2.choice(np.arange(n), p=q)
+        g2 = int(np.searchsorted(O.choice_cdf(q), rng2.next(), side="right"))
+        assert e2 == g2
+
+
+def test_uniform_and_float32_sum_restatements():
+    g = np.random.default_rng(8)
+    for _ in range(200):
+        seed = int(g.integers(0, 2 ** 31))
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        assert a.uniform(low=1e-7, high=2e-7, size=1)[0] == np.float64(1e-7) + np.float64(2e-7 - 1e-7) * b.random_sample()
+    # float32 add.reduce order (what the CUDA kernels and the oracle rely on): plain loop below 8, 8-way pairwise above
+    def pairwise(x):
+        n = len(x)
+        if n < 8:
+            r = np.float32(0)
+            for v in x:
+                r = np.float32(r + v)
+            return r
+        r = [np.float32(v) for v in x[:8]]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = np.float32(r[j] + x[i + j])
+            i += 8
+        res = np.float32(np.float32(np.float32(r[0] + r[1]) + np.float32(r[2] + r[3])) +
+                         np.float32(np.float32(r[4] + r[5]) + np.float32(r[6] + r[7])))
+        while i < n:
+            res = np.float32(res + x[i])
+            i += 1
+        return res
+    for n in range(1, 33):
+        for _ in range(40):
+            x = g.random(n).astype(np.float32)
+            assert x.sum() == pairwise(x), f"numpy float32 sum order changed for n={n}"
+            assert x.mean() == np.float32(pairwise(x) / np.float32(n))

@@ -55,3 +55,20 @@ def test_batched_selfplay_loop_on_device():
     d = out["dones"][:-1]
     nxt = out["observations"][1:][d]
     assert (nxt.abs() <= 0.05 + 1e-6).all()
+
+
+@pytest.mark.gpu
+def test_reanalyse_recomputes_targets_for_stored_positions():
+    from stochastic_muzero_b200 import ModelShape, Monte_carlo_tree_search, PackedModel, random_blob
+    from stochastic_muzero_b200.selfplay import reanalyse
+    shape = ModelShape(4, 2, 2, 61, 126, 4)
+    model = PackedModel(random_blob(shape, 0), shape)
+    mcts = Monte_carlo_tree_search(discount=0.997, num_simulations=10, maxium_action_sample=2, net="fp32", seed=2)
+    obs = torch.randn(6, 50, 4)
+    out = reanalyse(mcts, model, obs, chunk=128)
+    assert out["child_visits"].shape == (6, 50, 2) and out["root_values"].shape == (6, 50)
+    assert torch.allclose(out["child_visits"].sum(2), torch.ones(6, 50, dtype=torch.float64, device="cuda"))
+    # position (t, b) is searched as an independent tree: same answer as searching it alone with the same draws
+    mcts2 = Monte_carlo_tree_search(discount=0.997, num_simulations=10, maxium_action_sample=2, net="fp32", seed=2)
+    first = mcts2.run_batch(obs.reshape(300, 4)[:128], model, train=True)
+    assert torch.equal(first.select_actions(0.0)["stored_policy"].reshape(-1, 2), out["child_visits"].reshape(-1, 2)[:128])
