@@ -179,7 +179,10 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
 }
 // store 8 consecutive K values of row r (already bf16-packed) into the canonical A operand
 __device__ __forceinline__ void a_store(unsigned char* a, int r, int kchunk, uint4 v) {
-  *reinterpret_cast<uint4*>(a + kchunk * CHUNK_A + r * 16) = v;
+  // explicit st.shared (not a generic store): the .shared::cta proxy fence that follows must cover it
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(a + kchunk * CHUNK_A + r * 16)), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
 }
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -382,9 +385,11 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       if (l + 1 < ch.n_layers) mbar_wait(&sm.wbar[(l + 1) & 1], ((l + 1) >> 1) & 1);
     }
     mbar_wait(&sm.mbar, l & 1);
+    __syncwarp();       // tcgen05.ld below is .sync.aligned: reconverge after the spin loop
     if (stamp) job.timeline[1 + l * 4 + 2] = clock64();
     tc_fence_after();
     if (tid == 0 && l + 2 < ch.n_layers) load_weights(l + 2);   // ring slot l&1 is free again
+    __syncwarp();
     const float* bias = sm.bias[l] + c0;
 
     uint4 pend[4];                 // bf16 row pieces whose global store is deferred past the barrier
@@ -522,6 +527,286 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       __syncwarp();
       select_phase(g, a, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K-pipelined chain (simulation step only).  A dedicated issuer warp feeds the tensor core; the 16 epilogue warps
+// walk each hidden layer in four ROUNDS of 32 output columns (every warp takes an 8-column slice of the round for
+// its 32 rows).  When a round's columns of layer l are in the A operand, the issuer launches the two K-steps of
+// layer l+1 that consume exactly those columns — the MMA issue (~76 cycles per instruction) and most of the
+// commit -> wake-up latency disappear under the epilogue instead of following it.  Accumulators are
+// double-buffered in TMEM (columns [0,128) / [128,256) for even / odd layers); there is no CTA-wide barrier on
+// the hidden-layer path:
+//   named barrier 2+c  "columns 32c..32c+31 of the next layer's A operand are written": the 512 epilogue threads
+//                      bar.arrive (non-blocking), the issuer warp bar.sync's
+//   dbar[b]            "accumulator buffer b holds a finished layer"  (tcgen05.commit -> mbarrier)
+// Two things learnt the hard way (profiles/r1_bf16_ncu_summary.md): (1) the issuer loop must be walked by the
+// WHOLE warp with one lane issuing — a loop run by a single lane lets ptxas move loop-carried operands to uniform
+// registers with plain R2UR; (2) handing the A operand over through an mbarrier (arrive by the writers, try_wait
+// by the issuer) gave stale / garbage operand rows on B200 no matter which proxy fences were added on either
+// side, while the same hand-off through a named barrier is correct — so named barriers it is.
+// ---------------------------------------------------------------------------------------------
+constexpr int NEPI = NTHREADS;            // 512 epilogue threads
+constexpr int NPIPE = NTHREADS + 32;      // + issuer warp
+
+struct SmemPipe {
+  alignas(1024) unsigned char a[A_BYTES];
+  alignas(1024) unsigned char w[2][W_BYTES];
+  float bias[MAXL][TN];
+  unsigned long long wbar[2];
+  unsigned long long dbar[2];
+  unsigned long long bbar;
+  unsigned int tmem_base;
+  float4 part[4][TM];
+};
+
+__device__ __forceinline__ void epi_sync() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
+// producer / consumer split of a named barrier: the 512 epilogue threads arrive (non-blocking), the issuer warp waits
+__device__ __forceinline__ void nb_arrive(int id) { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NPIPE) : "memory"); }
+__device__ __forceinline__ void nb_sync(int id) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NPIPE) : "memory"); }
+__device__ __forceinline__ void tmem_ld8_nowait(unsigned taddr, unsigned* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(NPIPE, 1)
+k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  extern __shared__ unsigned char smem_raw[];
+  SmemPipe& sm = *reinterpret_cast<SmemPipe*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer_warp = warp == NEPI / 32;
+  const int r = (warp & 3) * 32 + lane;   // epilogue role: row of the tile == TMEM lane
+  const int cb = (warp >> 2) & 3;         // head layers: 32-column block; hidden layers: 8-column slice of a round
+
+  int tile = blockIdx.x;
+  const int T = (job.n_rows + TM - 1) / TM;
+  const int branch = tile >= T;
+  tile -= branch * T;
+  const Chain& ch = branch ? chain1 : chain0;
+  const int nl = ch.n_layers;
+  long long* tl = (job.timeline && blockIdx.x == 0 && lane == 0) ? job.timeline : nullptr;   // debug stamps
+  if (tl && tid == 0) tl[0] = clock64();
+
+  auto load_weights = [&](int l) {
+    const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[l & 1], bytes);
+    bulk_g2s(sm.w[l & 1], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
+  };
+  if (tid == 0) {
+    mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
+    mbar_init(&sm.dbar[0], 1); mbar_init(&sm.dbar[1], 1);
+    mbar_init(&sm.bbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bbytes = (unsigned)nl * TN * 4;
+    mbar_expect_tx(&sm.bbar, bbytes);
+    bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
+    load_weights(0);
+    if (nl > 1) load_weights(1);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(2 * TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  smz_pdl_launch_dependents();
+  smz_pdl_wait();
+  const int count = a.branch_count[sim * 2 + branch];
+  if (tile * TM >= count) {        // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
+    if (tid == 0) {
+      mbar_wait(&sm.bbar, 0);
+      mbar_wait(&sm.wbar[0], 0);
+      if (nl > 1) mbar_wait(&sm.wbar[1], 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(2 * TN) : "memory");
+    return;
+  }
+  // TMEM address + barrier inits become visible to everybody here
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = sm.tmem_base;
+
+  if (is_issuer_warp) {
+    // =========================== issuer warp: weights ring + tcgen05.mma =======================================
+    const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A, 128);
+    for (int l = 0; l < nl; ++l) {
+      const int nk = ch.layer[l].K / 16;
+      mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
+      const unsigned long long bd = umma_desc(s32(sm.w[l & 1]), CHUNK_W, 128);
+      const unsigned d = tmem + (unsigned)((l & 1) * TN);
+      for (int c = 0; c < 4; ++c) {
+        // A columns 32c..32c+31 of this layer are in shared memory.  Every barrier is consumed for every layer
+        // (also for column blocks a short-K layer does not read): arrivals and waits stay paired.
+        nb_sync(2 + c);
+        if (tl && c == 0) tl[1 + l * 4 + 0] = clock64();
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 2 * c; k < 2 * c + 2; ++k)
+            if (k < nk)
+              umma(d, ad + (unsigned long long)(k * ((2 * CHUNK_A) >> 4)), bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)),
+                   k > 0 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(&sm.dbar[l & 1]);
+      if (tl) tl[1 + l * 4 + 1] = clock64();
+      __syncwarp();
+      if (l + 2 < nl) {                           // ring slot l&1 is reusable once these MMAs have completed
+        mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
+        if (lane == 0) load_weights(l + 2);
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== epilogue warps =================================================================
+    const int row = tile * TM + r;
+    const bool valid = row < count;
+    int index = -1;
+    {   // stage the first A operand: thread (r, cb) fills K-chunks 2cb, 2cb+1 (+ its share of the one-hot chunks)
+      const __nv_bfloat16* src16 = nullptr;
+      int act = -1;
+      if (valid) {
+        const int4 rec = a.rows4[smz_row_index(a, sim, branch, row)];
+        index = rec.x;
+        src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + index) * SMZ_SP;
+        act = rec.z;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int kc = cb * 2 + q;
+        a_store(sm.a, r, kc, valid ? *reinterpret_cast<const uint4*>(src16 + kc * 8) : make_uint4(0, 0, 0, 0));
+      }
+      for (int kc = cb; kc < ch.onehot_pad / 8; kc += 4) {
+        unsigned w4[4] = {0, 0, 0, 0};
+        if (valid && act >= kc * 8 && act < kc * 8 + 8) {
+          const int j = act - kc * 8;
+          w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;
+        }
+        a_store(sm.a, r, 8 + kc, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+      }
+    }
+    fence_async_smem();
+    for (int c = 0; c < 4; ++c) nb_arrive(2 + c);
+    mbar_wait(&sm.bbar, 0);
+    const unsigned lane_t = tmem + ((unsigned)((warp & 3) * 32) << 16);
+    const int S = job.S;
+
+    for (int l = 0; l < nl; ++l) {
+      const int kind = ch.layer[l].kind;
+      const unsigned dcol = (unsigned)((l & 1) * TN);
+      mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
+      if (tl && warp == 0) tl[1 + l * 4 + 2] = clock64();
+      __syncwarp();
+      tc_fence_after();
+      if (kind == LK_HIDDEN) {
+        // four rounds of 32 columns; this warp owns columns 32c + 8*cb .. +7 of round c for its 32 rows
+        const int j8 = cb * 8;
+        unsigned raw[4][8];
+        // all four slices are requested at once (one exposed TMEM latency per layer, not four)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld8_nowait(lane_t + dcol + c * 32 + j8, raw[c]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float* bias = sm.bias[l] + c * 32 + j8;
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = elu_fast(__uint_as_float(raw[c][i]) + bias[i]);
+          a_store(sm.a, r, c * 4 + cb, make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                                  pack_bf16(x[6], x[7])));
+          fence_async_smem();
+          if (c == 3) tc_fence_before();
+          nb_arrive(2 + c);
+        }
+      } else {
+        // head layers are not pipelined: row-wise reductions need all columns.  Same code as k_bf16_chain,
+        // warp (quarter, cb) owns the 32-column block cb of its rows; barriers among the epilogue warps only.
+        const int c0 = cb * 32;
+        const float* bias = sm.bias[l] + c0;
+        uint4 pend[4];
+        uint4* pend_dst = nullptr;
+        float x[32];
+        tmem_ld32(lane_t + dcol + c0, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] += bias[i];
+        const bool state_seg = (kind == LK_STATE || kind == LK_STATE_REWARD) && cb < 2;
+        const bool soft_seg = (kind == LK_STATE_REWARD && cb >= 2) || (kind == LK_PRED && cb < 2);
+        SoftPart sp{-1e30f, 0.f, 0.f};
+        if (state_seg) {
+          float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { lo = fminf(lo, x[i]); hi = fmaxf(hi, x[i]); }
+          sm.part[cb][r] = make_float4(lo, hi, 0.f, 0.f);
+        } else if (soft_seg) {
+          sp = soft_part(x, c0 & 63, S);
+          sm.part[cb][r] = make_float4(sp.m, sp.z, sp.y, 0.f);
+        }
+        epi_sync();
+        if (state_seg) {
+          const float4 o = sm.part[cb ^ 1][r];
+          const float lo = fminf(sm.part[cb][r].x, o.x), hi = fmaxf(sm.part[cb][r].y, o.y);
+          float scale = hi - lo;
+          if (scale < 1e-5f) scale += 1e-5f;
+          const float inv = 1.f / scale;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = (x[i] - lo) * inv;
+          if (index >= 0 && job.hidden16_dst) pend_dst = reinterpret_cast<uint4*>(job.hidden16_dst + (size_t)index * SMZ_SP + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            pend[q] = make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                 pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+            a_store(sm.a, r, cb * 4 + q, pend[q]);
+          }
+        } else if (soft_seg && (cb & 1) == 0) {
+          const float4 o = sm.part[cb + 1][r];
+          const float v = support_scalar(sp, SoftPart{o.x, o.y, o.z});
+          float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
+          if (index >= 0 && dst) dst[index] = v;
+        } else if (kind == LK_PRED && cb == 2) {
+          const int n = ch.n_policy;
+          float m = -1e30f, z = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, x[i]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            x[i] = ex2f((x[i] - m) * 1.4426950408889634f);
+            z += x[i];
+          }
+          if (index >= 0 && job.policy_dst) {
+            float* dst = job.policy_dst + (size_t)index * job.pstride;
+            const float inv = 1.f / z;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < n) dst[i] = x[i] * inv;
+          }
+        }
+        if (l + 1 < nl) {
+          // the next network's A operand (K = 64: column blocks 0, 1); the other two barriers are consumed as well
+          fence_async_smem();
+          tc_fence_before();
+          for (int c = 0; c < 4; ++c) nb_arrive(2 + c);
+        }
+        if (pend_dst) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pend_dst[q] = pend[q];
+        }
+      }
+      if (tl && warp == 0) tl[1 + l * 4 + 3] = clock64();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TN) : "memory");
   }
 }
 
@@ -705,9 +990,11 @@ k_search_mega(SmzArena a, Chain chA, Chain chD, int n_trees, int first, int n_si
         if (gl + 1 < total) mbar_wait(&sm.wbar[(gl + 1) & 1], ((gl + 1) >> 1) & 1);
       }
       mbar_wait(&sm.mbar, gl & 1);
+      __syncwarp();
       if (stamp) timeline[1 + l * 4 + 2] = clock64();
       tc_fence_after();
       if (tid == 0 && gl + 2 < total) load_weights(gl + 2);
+      __syncwarp();
       const float* bias = sm.bias[br][l] + c0;
 
       uint4 pend[4];
@@ -866,6 +1153,7 @@ struct SmzBf16Image {
   int smem_bytes;
   long long* timeline;    // device debug buffer or null (SMZ_BF16_TIMELINE=1)
   int timeline_mega;
+  int use_pipe;           // K-pipelined chain for the simulation step (SMZ_NO_PIPE=1 turns it off)
 };
 
 static int round16(int v) { return (v + 15) / 16 * 16; }
@@ -910,6 +1198,8 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   }
   im->bias_pool = (float*)p;
   im->smem_bytes = (int)sizeof(Smem) + 1024;
+  cudaFuncSetAttribute((const void*)k_bf16_chain_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
+  im->use_pipe = getenv("SMZ_NO_PIPE") ? 0 : 1;
   if (getenv("SMZ_BF16_TIMELINE")) {
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
     cudaMemset(im->timeline, 0, (1 + 4 * MAXL + 16) * sizeof(long long));
@@ -1045,6 +1335,10 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   job.timeline = im->timeline;
   const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
+  if (tree_mode == 0 && im->use_pipe) {
+    smz_launch(k_bf16_chain_pipe, grid, dim3(NPIPE), sizeof(SmemPipe) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    return;
+  }
   auto* k = tree_mode == 2 ? k_bf16_chain<2> : (tree_mode == 1 ? k_bf16_chain<1> : k_bf16_chain<0>);
   smz_launch(k, grid, block, (size_t)im->smem_bytes, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
 }
