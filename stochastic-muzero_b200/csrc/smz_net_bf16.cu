@@ -532,8 +532,8 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 
 // ---------------------------------------------------------------------------------------------
 // K-pipelined chain (simulation step only).  A dedicated issuer warp feeds the tensor core; the 16 epilogue warps
-// walk each hidden layer in four ROUNDS of 32 output columns (every warp takes an 8-column slice of the round for
-// its 32 rows).  When a round's columns of layer l are in the A operand, the issuer launches the two K-steps of
+// walk each hidden layer in ROUNDS of 64 (or 32) output columns (every warp takes a 16- (8-) column slice of the
+// round for its 32 rows).  When a round's columns of layer l are in the A operand, the issuer launches the two K-steps of
 // layer l+1 that consume exactly those columns — the MMA issue (~76 cycles per instruction) and most of the
 // commit -> wake-up latency disappear under the epilogue instead of following it.  Accumulators are
 // double-buffered in TMEM (columns [0,128) / [128,256) for even / odd layers); there is no CTA-wide barrier on
@@ -572,6 +572,10 @@ __device__ __forceinline__ void tmem_ld8_nowait(unsigned taddr, unsigned* r) {
                : "memory");
 }
 
+// NR = rounds per hidden layer: 2 = 64-column rounds, 16-column slices per warp (default: every round costs a proxy
+// fence, two rounds measured best); 4 = 32-column rounds, 8-column slices.  An uneven 96 + 32 split (fewer K-steps
+// left after the last round) measured slower than 64 + 64.
+template <int NR>
 __global__ void __launch_bounds__(NPIPE, 1)
 k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
@@ -642,15 +646,15 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
       const unsigned long long bd = umma_desc(s32(sm.w[l & 1]), CHUNK_W, 128);
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
-      for (int c = 0; c < 4; ++c) {
-        // A columns 32c..32c+31 of this layer are in shared memory.  Every barrier is consumed for every layer
+      for (int c = 0; c < NR; ++c) {
+        // the A columns of round c of this layer are in shared memory.  Every barrier is consumed for every layer
         // (also for column blocks a short-K layer does not read): arrivals and waits stay paired.
         nb_sync(2 + c);
         if (tl && c == 0) tl[1 + l * 4 + 0] = clock64();
         tc_fence_after();
         if (lane == 0) {
 #pragma unroll
-          for (int k = 2 * c; k < 2 * c + 2; ++k)
+          for (int k = (8 / NR) * c; k < (8 / NR) * (c + 1); ++k)
             if (k < nk)
               umma(d, ad + (unsigned long long)(k * ((2 * CHUNK_A) >> 4)), bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)),
                    k > 0 ? 1u : 0u);
@@ -695,7 +699,7 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       }
     }
     fence_async_smem();
-    for (int c = 0; c < 4; ++c) nb_arrive(2 + c);
+    for (int c = 0; c < NR; ++c) nb_arrive(2 + c);
     mbar_wait(&sm.bbar, 0);
     const unsigned lane_t = tmem + ((unsigned)((warp & 3) * 32) << 16);
     const int S = job.S;
@@ -708,23 +712,31 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       __syncwarp();
       tc_fence_after();
       if (kind == LK_HIDDEN) {
-        // four rounds of 32 columns; this warp owns columns 32c + 8*cb .. +7 of round c for its 32 rows
-        const int j8 = cb * 8;
-        unsigned raw[4][8];
-        // all four slices are requested at once (one exposed TMEM latency per layer, not four)
+        // NR rounds of 128/NR columns; this warp owns a (32/NR)-column slice of every round for its 32 rows
+        constexpr int SL = 32 / NR;              // slice width: 8 or 16 columns
+        constexpr int RC = TN / NR;              // columns per round
+        const int j0 = cb * SL;
+        unsigned raw[NR][SL];
+        // all slices are requested at once (one exposed TMEM latency per layer)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld8_nowait(lane_t + dcol + c * 32 + j8, raw[c]);
+        for (int c = 0; c < NR; ++c) {
+          if constexpr (NR == 4) tmem_ld8_nowait(lane_t + dcol + c * RC + j0, raw[c]);
+          else tmem_ld16_nowait(lane_t + dcol + c * RC + j0, raw[c]);
+        }
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float* bias = sm.bias[l] + c * 32 + j8;
-          float x[8];
+        for (int c = 0; c < NR; ++c) {
+          const float* bias = sm.bias[l] + c * RC + j0;
+          float x[SL];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = elu_fast(__uint_as_float(raw[c][i]) + bias[i]);
-          a_store(sm.a, r, c * 4 + cb, make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                                  pack_bf16(x[6], x[7])));
+          for (int i = 0; i < SL; ++i) x[i] = elu_fast(__uint_as_float(raw[c][i]) + bias[i]);
+#pragma unroll
+          for (int q = 0; q < SL / 8; ++q)
+            a_store(sm.a, r, (c * RC + j0) / 8 + q,
+                    make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                               pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
           fence_async_smem();
-          if (c == 3) tc_fence_before();
+          if (c == NR - 1) tc_fence_before();
           nb_arrive(2 + c);
         }
       } else {
@@ -793,7 +805,7 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           // the next network's A operand (K = 64: column blocks 0, 1); the other two barriers are consumed as well
           fence_async_smem();
           tc_fence_before();
-          for (int c = 0; c < 4; ++c) nb_arrive(2 + c);
+          for (int c = 0; c < NR; ++c) nb_arrive(2 + c);
         }
         if (pend_dst) {
 #pragma unroll
@@ -1152,6 +1164,7 @@ struct SmzBf16Image {
   size_t pool_bytes;
   int smem_bytes;
   long long* timeline;    // device debug buffer or null (SMZ_BF16_TIMELINE=1)
+  int pipe_rounds;        // 2 (default) or 4 rounds per hidden layer in the pipelined kernel (SMZ_PIPE_ROUNDS)
   int timeline_mega;
   int use_pipe;           // K-pipelined chain for the simulation step (SMZ_NO_PIPE=1 turns it off)
 };
@@ -1198,8 +1211,10 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   }
   im->bias_pool = (float*)p;
   im->smem_bytes = (int)sizeof(Smem) + 1024;
-  cudaFuncSetAttribute((const void*)k_bf16_chain_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   im->use_pipe = getenv("SMZ_NO_PIPE") ? 0 : 1;
+  im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
     cudaMemset(im->timeline, 0, (1 + 4 * MAXL + 16) * sizeof(long long));
@@ -1336,7 +1351,8 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   job.timeline = im->timeline;
   const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
   if (tree_mode == 0 && im->use_pipe) {
-    smz_launch(k_bf16_chain_pipe, grid, dim3(NPIPE), sizeof(SmemPipe) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    auto* kp = im->pipe_rounds == 4 ? k_bf16_chain_pipe<4> : k_bf16_chain_pipe<2>;
+    smz_launch(kp, grid, dim3(NPIPE), sizeof(SmemPipe) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
     return;
   }
   auto* k = tree_mode == 2 ? k_bf16_chain<2> : (tree_mode == 1 ? k_bf16_chain<1> : k_bf16_chain<0>);
