@@ -42,6 +42,8 @@ struct smz_engine {
   SmzBf16Image* bf16;    // tcgen05 path state (null unless net_mode == SMZ_NET_BF16)
   SmzVisionImage* vision;  // vision family state (null unless net_mode == SMZ_NET_VISION)
   double* pbc_dev;
+  double* rcp64_dev;
+  float* rcp32_dev;
   unsigned long long* seed_dev;
   signed char* sign_dev;
   std::vector<int32_t> to_play_tab;   // [n_phases][N+2], host copy for export
@@ -68,6 +70,8 @@ static cudaError_t dev_alloc(smz_engine* e, T** p, size_t n) {
   return r;
 }
 
+static int rcp_entries(int n_sims) { return n_sims + 3 > SMZ_MAX_POLICY + 1 ? n_sims + 3 : SMZ_MAX_POLICY + 1; }
+
 static int fill_default_tables(smz_engine* e) {
   const smz_config& c = e->cfg;
   const int n = c.num_simulations + 2;
@@ -75,6 +79,12 @@ static int fill_default_tables(smz_engine* e) {
   for (int i = 0; i < n; ++i)
     pbc[i] = sqrt((double)i) * (log(((double)i + (double)c.pb_c_base + 1.0) / (double)c.pb_c_base) + c.pb_c_init);
   CU(cudaMemcpy(e->pbc_dev, pbc.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  const int nt = rcp_entries(c.num_simulations);     // divisors: visit counts <= N + 2 and child counts <= 32
+  std::vector<double> r64(nt, 0.0);
+  std::vector<float> r32(nt, 0.f);
+  for (int i = 1; i < nt; ++i) { r64[i] = 1.0 / (double)i; r32[i] = 1.0f / (float)i; }   // IEEE: correctly rounded
+  CU(cudaMemcpy(e->rcp64_dev, r64.data(), nt * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->rcp32_dev, r32.data(), nt * sizeof(float), cudaMemcpyHostToDevice));
   std::vector<signed char> sign(n, 1);
   CU(cudaMemcpy(e->sign_dev, sign.data(), n, cudaMemcpyHostToDevice));
   e->to_play_tab.assign(n, 0);
@@ -161,6 +171,8 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
     ALLOC(a.rec_branch, B * a.N); ALLOC(a.rec_root_policy, B * a.W);
   }
   ALLOC(e->pbc_dev, (size_t)a.N + 2);
+  ALLOC(e->rcp64_dev, (size_t)rcp_entries(a.N));
+  ALLOC(e->rcp32_dev, (size_t)rcp_entries(a.N));
   ALLOC(e->seed_dev, 2);
   ALLOC(e->sign_dev, (size_t)a.N + 2);
   if (c.net_mode == SMZ_NET_VISION) {
@@ -183,6 +195,8 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
     return fail(SMZ_E_CUDA, "smz_create: cudaMalloc failed: %s", cudaGetErrorString(r));
   }
   a.pbc = e->pbc_dev;
+  a.rcp64 = e->rcp64_dev;
+  a.rcp32 = e->rcp32_dev;
   a.seed_state = e->seed_dev;
   a.sign = e->sign_dev;
   int rc = fill_default_tables(e);

@@ -63,6 +63,8 @@ struct SmzArena {
   const unsigned long long* seed_state;  // device [2]: {Philox key, global id of local tree 0}
   // constants
   const double* pbc;         // [N+2]: sqrt(n) * (log((n + base + 1)/base) + init)
+  const double* rcp64;       // [N+3]: correctly rounded 1/n (n >= 1): exact small-integer divisions without DDIV
+  const float* rcp32;        // [N+3]: the same in float32
   const signed char* sign;   // [n_phases][N+2]
   float discount;
   float one_minus_frac_f32;  // f32(1 - frac), the weak-scalar cast the reference performs
@@ -122,12 +124,17 @@ struct SmzRng {
   const double* tape;
   unsigned long long seed, tree0;
   int* err;
+  // optional window of uniforms [win_base, win_base + win_len) of THIS thread's tree, generated ahead of time
+  // (k_backup_select_sm fills it while the network step is still running)
+  const double* win;
+  int win_base, win_len;
 };
 __device__ __forceinline__ SmzRng smz_make_rng(const SmzArena& a) {
   SmzRng r;
   r.mode = a.rng_mode; r.stride = a.tape_stride; r.tape = a.tape_u; r.err = a.error_flag;
   r.seed = a.rng_mode ? 0ull : a.seed_state[0];
   r.tree0 = a.rng_mode ? 0ull : a.seed_state[1];
+  r.win = nullptr; r.win_base = 0; r.win_len = 0;
   return r;
 }
 __device__ __forceinline__ double smz_rng_uniform(const SmzRng& r, int tree, int idx) {
@@ -135,6 +142,20 @@ __device__ __forceinline__ double smz_rng_uniform(const SmzRng& r, int tree, int
     if (idx >= r.stride) { *r.err = 1; return 0.5; }
     return r.tape[(size_t)tree * r.stride + idx];
   }
+  if (r.win && (unsigned)(idx - r.win_base) < (unsigned)r.win_len) return r.win[idx - r.win_base];
   return smz_philox_uniform(r.seed, r.tree0 + (unsigned long long)tree, (unsigned)idx, 0u);
+}
+
+// Exact division through a correctly rounded reciprocal (Markstein): q = RN(x*r), rem = x - q*d (exact, one FMA),
+// RN(q + rem*r) == RN(x/d) whenever r == RN(1/d), q is faithful and d's significand is not all ones — true for
+// the small integers (visit counts, child counts) tabulated in rcp64 / rcp32.  Three dependent instructions
+// instead of the ~40 of a software DDIV; checked against IEEE division in tests/test_host_logic.py.
+__device__ __forceinline__ double smz_div_r64(double x, double d, double r) {
+  const double q = __dmul_rn(x, r);
+  return __fma_rn(__fma_rn(-q, d, x), r, q);
+}
+__device__ __forceinline__ float smz_div_r32(float x, float d, float r) {
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-q, d, x), r, q);
 }
 #endif

@@ -280,8 +280,10 @@ k_bf16_chain(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   }
 
   // ---- everything above is independent of the previous kernel; from here on we read its results ---
-  smz_pdl_launch_dependents();
   smz_pdl_wait();
+  // only now may the tree kernel of this simulation start: its prologue mirrors the tree arena into shared memory,
+  // which the PREVIOUS tree kernel (complete once the wait above returns) was still writing
+  smz_pdl_launch_dependents();
   int count = job.n_rows;
   if (job.input_kind == IN_GATHER) count = a.branch_count[sim * 2 + branch];
   const int row = tile * TM + r;
@@ -616,8 +618,10 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  smz_pdl_launch_dependents();
   smz_pdl_wait();
+  // only now may the tree kernel of this simulation start: its prologue mirrors the tree arena into shared memory,
+  // which the PREVIOUS tree kernel (complete once the wait above returns) was still writing
+  smz_pdl_launch_dependents();
   const int count = a.branch_count[sim * 2 + branch];
   if (tile * TM >= count) {        // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
     if (tid == 0) {

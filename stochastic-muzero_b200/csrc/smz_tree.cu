@@ -10,6 +10,8 @@
 //   k_select         :235-267   pUCT argmax / chance sampling descent, leaf record, branch compaction
 //   k_expand_backup  :289-308   children of the leaf + min-max discounted backup
 //   k_read_roots     game.py:179-204 consumer view (child visits, priors, rewards, root value)
+#include <stdlib.h>
+
 #include "smz_common.cuh"
 #include "smz_kernels.h"
 #include "smz_tree_dev.cuh"
@@ -103,6 +105,72 @@ __global__ void k_backup_select(SmzArena a, int n_trees, int sim) {
   __syncwarp();
   if (stamp) a.dbg[1] = clock64();
   select_phase(g, a, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr);
+  if (stamp) { a.dbg[2] = clock64(); a.dbg[3] = a.path_len[tree]; }
+}
+
+// Same step with every tree's node records mirrored in shared memory.  The tree arena is written by tree kernels
+// only, so the mirror is filled BEFORE griddepcontrol.wait — while the network step is still running (the network
+// kernels signal their dependents only after their own wait, so the previous tree kernel has completed).  After
+// the wait the phases touch L2 for the network outputs alone: expansion and backup update mirror + arena, the
+// descent reads the mirror (shared-memory latency per level instead of an L2 round trip).
+constexpr int SMZ_UWIN = 32;     // uniforms generated ahead per tree (Philox mode): expansion draws + ~12 levels of descent
+
+// dynamic shared memory of k_backup_select_sm for `tpb` trees per block (must match the kernel's carve-up)
+__host__ __device__ inline size_t smz_mirror_bytes(int tpb, int M, int A, int n_tab, int n_pbc) {
+  size_t b = (size_t)tpb * M * (sizeof(int4) + sizeof(int2));          // node records
+  b += (size_t)tpb * (A + SMZ_UWIN) * sizeof(double);                    // root priors, uniform window
+  b += (size_t)(n_pbc + n_tab) * sizeof(double) + (size_t)n_tab * sizeof(float);   // pbc, rcp64, rcp32
+  return b + 16;
+}
+
+template <int G>
+__global__ void k_backup_select_sm(SmzArena a, int n_trees, int sim, int n_tab) {
+  extern __shared__ int4 smz_sm_nodes[];
+  Group<G> g;
+  int tree = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool alive = tree < n_trees;
+  if (!alive) tree = n_trees - 1;
+  const int tpb = blockDim.x / G, lt = threadIdx.x / G;           // trees per block, local tree
+  // ---- carve-up: [stat][link][root priors][uniform window][pbc][rcp64][rcp32]
+  int4* sst = smz_sm_nodes + (size_t)lt * a.M;
+  int2* slk_all = reinterpret_cast<int2*>(smz_sm_nodes + (size_t)tpb * a.M);
+  int2* slk = slk_all + (size_t)lt * a.M;
+  double* dbl = reinterpret_cast<double*>(slk_all + (size_t)tpb * a.M + ((size_t)tpb * a.M & 1));
+  double* srp = dbl + (size_t)lt * a.A;
+  double* swin = dbl + (size_t)tpb * a.A + (size_t)lt * SMZ_UWIN;
+  double* spbc = dbl + (size_t)tpb * (a.A + SMZ_UWIN);
+  double* sr64 = spbc + (a.N + 2);
+  float* sr32 = reinterpret_cast<float*>(sr64 + n_tab);
+
+  // ---- prologue: everything here was written by tree kernels / the host, not by the running network step
+  SmzRng rng = smz_make_rng(a);
+  const int cursor0 = a.ucursor[tree];
+  {
+    const size_t tb = (size_t)tree * a.M;
+    const int used = 1 + a.A + sim * a.Kmax;                      // nodes allocated before this expansion
+    for (int i = g.gl; i < used; i += G) {
+      sst[i] = a.stat[tb + i];
+      slk[i] = a.link[tb + i];
+    }
+    for (int i = g.gl; i < a.A; i += G) srp[i] = a.root_prior[(size_t)tree * a.A + i];
+    for (int i = threadIdx.x; i < a.N + 2; i += blockDim.x) spbc[i] = a.pbc[i];
+    for (int i = threadIdx.x; i < n_tab; i += blockDim.x) { sr64[i] = a.rcp64[i]; sr32[i] = a.rcp32[i]; }
+    if (rng.mode == 0)                                            // device Philox: the draws depend on the cursor only
+      for (int i = g.gl; i < SMZ_UWIN; i += G) swin[i] = smz_rng_uniform(rng, tree, cursor0 + i);
+  }
+  SmzArena al = a;                                                // same arena, tables served from shared memory
+  al.pbc = spbc; al.rcp64 = sr64; al.rcp32 = sr32;
+  if (rng.mode == 0) { rng.win = swin; rng.win_base = cursor0; rng.win_len = SMZ_UWIN; }
+  smz_pdl_wait();                 // the network step of `sim` must have landed
+  smz_pdl_launch_dependents();    // the next network step may set itself up (barriers, TMEM, weights)
+  __syncthreads();
+  const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) a.dbg[0] = clock64();
+  const TreeState ts = expand_backup_phase<G, true>(g, al, rng, tree, alive, sim, a.out_policy, a.W, a.out_value, a.out_reward,
+                                                    sst, slk);
+  __syncwarp();
+  if (stamp) a.dbg[1] = clock64();
+  select_phase<G, true, true>(g, al, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr, sst, slk, srp);
   if (stamp) { a.dbg[2] = clock64(); a.dbg[3] = a.path_len[tree]; }
 }
 
@@ -249,7 +317,27 @@ void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim
                             a, n_trees, sim, policy, pstride, value, reward)));
 }
 
+// shared-memory mirror: node records of (trees per block) trees + tables must fit; SMZ_NO_TREE_SMEM=1 keeps the
+// arena-only kernel
+static int rcp_entries(const SmzArena& a) { return a.N + 3 > SMZ_MAX_POLICY + 1 ? a.N + 3 : SMZ_MAX_POLICY + 1; }
+static size_t mirror_bytes(const SmzArena& a, int lanes) {
+  return smz_mirror_bytes(kThreads / lanes, a.M, a.A, rcp_entries(a), a.N + 2);
+}
+
+bool smz_tree_mirror_fits(const SmzArena& a, int lanes) {
+  static const bool off = getenv("SMZ_NO_TREE_SMEM") != nullptr;
+  return !off && mirror_bytes(a, lanes) <= 96 * 1024;
+}
+
 void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s) {
+  if (smz_tree_mirror_fits(a, lanes)) {
+    const size_t smem = mirror_bytes(a, lanes);
+    SMZ_DISPATCH_G(lanes, (cudaFuncSetAttribute((const void*)k_backup_select_sm<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem),
+                           smz_launch(k_backup_select_sm<G>, dim3(grid_for<G>(n_trees, kThreads)), dim3(kThreads), smem, s, pdl,
+                                      a, n_trees, sim, rcp_entries(a))));
+    return;
+  }
   SMZ_DISPATCH_G(lanes, (smz_launch(k_backup_select<G>, dim3(grid_for<G>(n_trees, kThreads)), dim3(kThreads), 0, s, pdl,
                                     a, n_trees, sim)));
 }

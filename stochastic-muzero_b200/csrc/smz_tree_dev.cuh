@@ -128,10 +128,11 @@ struct TreeState {
 // while descending, so the backup needs ONE round trip (the record) instead of two (index -> stat).
 // COMPACT: append the tree to the per-branch row list of the simulation (one atomic per tree) for kernels that
 // re-tile the leaves by branch; the persistent per-tile kernel sorts its own rows instead.
-template <int G, bool COMPACT = true>
+template <int G, bool COMPACT = true, bool MIRROR = false>
 __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree, bool alive,
                                              int sim, TreeState ts, int* __restrict__ o_slot, int* __restrict__ o_action,
-                                             int* __restrict__ o_branch) {
+                                             int* __restrict__ o_branch, const int4* __restrict__ sst = nullptr,
+                                             const int2* __restrict__ slk = nullptr, const double* __restrict__ srp = nullptr) {
   const size_t tb = (size_t)tree * a.M;
   int cursor = ts.cursor;
   const float vmin = ts.mm.x, vmax = ts.mm.y;
@@ -139,6 +140,11 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
 
   int depth = 0, cbase = 1, nch = a.A;
   int parent_visit = ts.root.x;
+  // min-max normalisation divides by the same range at every level: one correctly rounded reciprocal, then
+  // Markstein's exact division (smz_common.cuh); a range whose significand is all ones keeps the plain division
+  const float range = __fsub_rn(vmax, vmin);
+  const float rrange = vmax > vmin ? __frcp_rn(range) : 0.f;
+  const bool range_plain = (__float_as_int(range) & 0x7FFFFF) == 0x7FFFFF || range < 1e-30f;
   if (alive && g.gl == 0) path[0] = make_int4(0, ts.root.x, ts.root.y, 0);
   int L = 1, child = 0, child_key = 0;
   bool going = alive;
@@ -149,10 +155,15 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     int2 lk = make_int2(0, 0);
     double prior0 = 0.0, pbc = 0.0;
     if (act) {
-      st = a.stat[tb + cbase + g.gl];
-      lk = a.link[tb + cbase + g.gl];
-      if (depth == 0) prior0 = a.root_prior[(size_t)tree * a.A + g.gl];
-      if (!chance) pbc = __ldg(a.pbc + parent_visit);
+      if constexpr (MIRROR) {      // the tree's node records live in shared memory (k_backup_select_sm)
+        st = sst[cbase + g.gl];
+        lk = slk[cbase + g.gl];
+      } else {
+        st = a.stat[tb + cbase + g.gl];
+        lk = a.link[tb + cbase + g.gl];
+      }
+      if (depth == 0) prior0 = srp ? srp[g.gl] : a.root_prior[(size_t)tree * a.A + g.gl];
+      if (!chance) pbc = a.pbc[parent_visit];     // plain load: the table may live in shared memory
     }
     // the draw only depends on the cursor: it is computed while the loads are in flight
     const double u = (going && (chance || act)) ? smz_rng_uniform(rng, tree, chance ? cursor : cursor + g.gl) : 0.0;
@@ -161,7 +172,7 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       // chance node: sample a child from the smoothed priors (mcts.py:249-255, T9)
       const float p = __int_as_float(st.w);
       const float om = act ? __fadd_rn(__fsub_rn(1.f, p), 1e-12f) : 0.f;
-      const float rem = fabsf(__fdiv_rn(np_sum_f32(g, om, nch), (float)nch));
+      const float rem = fabsf(smz_div_r32(np_sum_f32(g, om, nch), (float)nch, a.rcp32[nch]));
       const float sh = act ? __fadd_rn(p, rem) : 0.f;
       const float tot = np_sum_f32(g, sh, nch);
       const float q = act ? __fdiv_rn(sh, tot) : 0.f;
@@ -177,12 +188,12 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       if (act && !chance) {
         const double prior = (depth == 0) ? prior0 : (double)__int_as_float(st.w);
         // pbc = sqrt(n) * pb_c(n), the left-associated head of mcts.py:237, tabulated by the host
-        const double ps = __ddiv_rn(__dmul_rn(pbc, prior), (double)(st.x + 1));
+        const double ps = smz_div_r64(__dmul_rn(pbc, prior), (double)(st.x + 1), a.rcp64[st.x + 1]);
         double vs = 0.0;
         if (st.x > 0) {
-          const float val = __fdiv_rn(__int_as_float(st.y), (float)st.x);
+          const float val = smz_div_r32(__int_as_float(st.y), (float)st.x, a.rcp32[st.x]);
           float v = __fadd_rn(__int_as_float(st.z), __fmul_rn(a.discount, val));
-          if (vmax > vmin) v = __fdiv_rn(__fsub_rn(v, vmin), __fsub_rn(vmax, vmin));
+          if (vmax > vmin) v = range_plain ? __fdiv_rn(__fsub_rn(v, vmin), range) : smz_div_r32(__fsub_rn(v, vmin), range, rrange);
           vs = (double)v;
         }
         const double noise = __dadd_rn(1e-7, __dmul_rn(2e-7 - 1e-7, u));
@@ -238,11 +249,12 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool MIRROR = false>
 __device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree,
                                                          bool alive, int sim, const float* __restrict__ policy,
                                                          int pstride, const float* __restrict__ value,
-                                                         const float* __restrict__ reward) {
+                                                         const float* __restrict__ reward, int4* __restrict__ sst = nullptr,
+                                                         int2* __restrict__ slk = nullptr) {
   const size_t tb = (size_t)tree * a.M;
   // everything this phase needs from memory is requested up front (one round trip): the leaf record,
   // the network outputs, the tree state and — speculatively — the first two chunks of path records
@@ -269,12 +281,20 @@ __device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, cons
     const int r = __popc(found & ((1u << g.gl) - 1u));
     a.stat[tb + cb + r] = make_int4(0, 0, 0, __float_as_int(p));
     a.link[tb + cb + r] = make_int2(0, g.gl);
+    if constexpr (MIRROR) {
+      sst[cb + r] = make_int4(0, 0, 0, __float_as_int(p));
+      slk[cb + r] = make_int2(0, g.gl);
+    }
   }
   const float rew = branch ? rew_in : 0.f;
   if (alive && g.gl == 0) {
     a.link[tb + leaf].x = cb;
     a.ucursor[tree] = cursor;
     if (branch) reinterpret_cast<int*>(a.stat + tb + leaf)[2] = __float_as_int(rew);     // Node.reward of the leaf
+    if constexpr (MIRROR) {
+      slk[leaf].x = cb;
+      if (branch) sst[leaf].z = __float_as_int(rew);
+    }
     if (a.rec_policy) {
       const size_t ro = ((size_t)tree * a.N + sim);
       for (int i = 0; i < a.W; ++i) a.rec_policy[ro * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
@@ -311,8 +331,9 @@ __device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, cons
       const float vs = __fadd_rn(__int_as_float(rec.z), (signed char)__ldg(sign + l) > 0 ? myv : -myv);
       const int2 upd = make_int2(rec.y + 1, __float_as_int(vs));
       *reinterpret_cast<int2*>(a.stat + tb + rec.x) = upd;          // {visit_count, value_sum}
+      if constexpr (MIRROR) *reinterpret_cast<int2*>(sst + rec.x) = upd;
       if (l == 0) root = upd;
-      const float nv = __fdiv_rn(vs, (float)upd.x);
+      const float nv = smz_div_r32(vs, (float)upd.x, a.rcp32[upd.x]);
       mm.x = fminf(mm.x, nv);
       mm.y = fmaxf(mm.y, nv);
     }

@@ -189,3 +189,33 @@ def test_uniform_and_float32_sum_restatements():
             x = g.random(n).astype(np.float32)
             assert x.sum() == pairwise(x), f"numpy float32 sum order changed for n={n}"
             assert x.mean() == np.float32(pairwise(x) / np.float32(n))
+
+
+def test_markstein_division_is_exact_for_tabulated_divisors():
+    """smz_div_r64 / smz_div_r32 (csrc/smz_common.cuh): q = RN(x*r); RN(q + (x - q*d)*r) with r = RN(1/d) must equal
+    IEEE division for the small-integer divisors the tree kernels tabulate (visit counts, child counts) and for the
+    min-max range divisor.  Checked here with exact rational arithmetic (an FMA rounds once)."""
+    from fractions import Fraction
+    import random
+
+    def rn32(fr):
+        f = np.float32(float(fr))
+        cands = [f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))]
+        return np.float32(min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1)))
+
+    rnd = random.Random(7)
+    for _ in range(4000):
+        d = rnd.randint(1, 64)
+        x = rnd.uniform(0, 4) * 10 ** rnd.uniform(-6, 2)
+        r = 1.0 / d
+        q = x * r
+        rem = float(Fraction(x) - Fraction(q) * d)                     # exact FMA, one rounding
+        assert float(Fraction(q) + Fraction(rem) * Fraction(r)) == x / d
+    for _ in range(4000):
+        d = np.float32(rnd.randint(1, 64)) if rnd.random() < 0.5 else np.float32(rnd.uniform(1e-3, 60))
+        x = np.float32(rnd.uniform(-50, 50))
+        r = np.float32(1.0) / d
+        q = np.float32(x * r)
+        rem = rn32(Fraction(float(x)) - Fraction(float(q)) * Fraction(float(d)))
+        got = rn32(Fraction(float(q)) + Fraction(float(rem)) * Fraction(float(r)))
+        assert got == np.float32(x / d), (x, d)
