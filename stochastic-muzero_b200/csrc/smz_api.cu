@@ -205,6 +205,8 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
     if (cudaMemcpy(e->seed_dev, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SMZ_E_CUDA, "seed upload failed");
   }
   if (rc == SMZ_OK && a.hidden) {
+    cudaMemset(a.rows, 0, 4 * B * sizeof(int));          // speculative gathers read rows beyond the live count
+    cudaMemset(a.rows4, 0, 4 * B * sizeof(int4));
     cudaError_t m = cudaMemset(a.hidden, 0, (size_t)(a.N + 1) * B * a.Sp * sizeof(float));
     if (m != cudaSuccess) rc = fail(SMZ_E_CUDA, "memset: %s", cudaGetErrorString(m));
   }

@@ -622,6 +622,18 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   // only now may the tree kernel of this simulation start: its prologue mirrors the tree arena into shared memory,
   // which the PREVIOUS tree kernel (complete once the wait above returns) was still writing
   smz_pdl_launch_dependents();
+  // The row record and the parent's hidden row are requested before the row count of this branch is known (three
+  // dependent L2 round trips become two): rows beyond the count hold stale but in-range records (zeroed at create).
+  int4 rec = make_int4(0, 0, 0, 0);
+  uint4 hrow[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  if (!is_issuer_warp) {
+    rec = a.rows4[smz_row_index(a, sim, branch, min(tile * TM + r, a.B - 1))];
+    rec.x = min(max(rec.x, 0), a.B - 1);
+    rec.y = min(max(rec.y, 0), a.N);
+    const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + rec.x) * SMZ_SP;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) hrow[q] = *reinterpret_cast<const uint4*>(src16 + (cb * 2 + q) * 8);
+  }
   const int count = a.branch_count[sim * 2 + branch];
   if (tile * TM >= count) {        // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
     if (tid == 0) {
@@ -678,21 +690,11 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     // =========================== epilogue warps =================================================================
     const int row = tile * TM + r;
     const bool valid = row < count;
-    int index = -1;
+    const int index = valid ? rec.x : -1;
     {   // stage the first A operand: thread (r, cb) fills K-chunks 2cb, 2cb+1 (+ its share of the one-hot chunks)
-      const __nv_bfloat16* src16 = nullptr;
-      int act = -1;
-      if (valid) {
-        const int4 rec = a.rows4[smz_row_index(a, sim, branch, row)];
-        index = rec.x;
-        src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + index) * SMZ_SP;
-        act = rec.z;
-      }
+      const int act = valid ? rec.z : -1;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int kc = cb * 2 + q;
-        a_store(sm.a, r, kc, valid ? *reinterpret_cast<const uint4*>(src16 + kc * 8) : make_uint4(0, 0, 0, 0));
-      }
+      for (int q = 0; q < 2; ++q) a_store(sm.a, r, cb * 2 + q, valid ? hrow[q] : make_uint4(0, 0, 0, 0));
       for (int kc = cb; kc < ch.onehot_pad / 8; kc += 4) {
         unsigned w4[4] = {0, 0, 0, 0};
         if (valid && act >= kc * 8 && act < kc * 8 + 8) {
