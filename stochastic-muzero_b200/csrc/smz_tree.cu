@@ -329,8 +329,20 @@ bool smz_tree_mirror_fits(const SmzArena& a, int lanes) {
   return !off && mirror_bytes(a, lanes) <= 96 * 1024;
 }
 
+// The mirror kernel is the low-latency variant (one block of 128 threads per SM or two); with many blocks per SM the
+// arena-only kernel wins on occupancy (measured crossover on B200, cfg-2 shapes: ~16 k trees = 512 blocks).
+static bool mirror_pays(int blocks) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return blocks <= 3 * sms;
+}
+
 void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s) {
-  if (smz_tree_mirror_fits(a, lanes)) {
+  if (smz_tree_mirror_fits(a, lanes) && mirror_pays((n_trees * lanes + kThreads - 1) / kThreads)) {
     const size_t smem = mirror_bytes(a, lanes);
     SMZ_DISPATCH_G(lanes, (cudaFuncSetAttribute((const void*)k_backup_select_sm<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem),
