@@ -829,6 +829,360 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 64-row tiles (chosen automatically for small batches, SMZ_M64=0/1 forces): the hidden-layer epilogue is bound by the MUFU pipe of the SM (128 x 128
+// exponentials per layer at 16 per clock), so a tile of 64 leaves per CTA on twice as many SMs halves it.
+// tcgen05.mma M = 64 puts accumulator row m in TMEM lane (m % 16) + 32 * (m / 16): every warp quarter owns 16 rows,
+// read with tcgen05.ld.16x256b so that all 32 lanes carry data (thread t: row t/4 and row t/4 + 8, two consecutive
+// columns per 8-column group — the m16n8 accumulator fragment).  Same issuer warp / rounds / named-barrier
+// structure as k_bf16_chain_pipe.
+// ---------------------------------------------------------------------------------------------
+constexpr int TM64 = 64;
+constexpr int A64_BYTES = TM64 * KMAX * 2;       // 16 KB
+constexpr int CHUNK_A64 = TM64 * 16;             // LBO of the 64-row A operand
+constexpr unsigned IDESC64 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TM64 >> 4) << 24);
+
+struct Smem64 {
+  alignas(1024) unsigned char a[A64_BYTES];
+  alignas(1024) unsigned char w[2][W_BYTES];
+  float bias[MAXL][TN];
+  unsigned long long wbar[2];
+  unsigned long long dbar[2];
+  unsigned long long bbar;
+  unsigned int tmem_base;
+  int rowidx[TM64];          // tree id of every tile row (-1 = none)
+  float4 part[4][TM64];
+};
+
+__device__ __forceinline__ void umma64(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(IDESC64), "r"(accum)
+      : "memory");
+}
+// 16 lanes x (8 * X) columns: 4 * X registers per thread, group g = regs 4g..4g+3 = {row t/4: cols 2(t%4), +1; row t/4+8: same}
+__device__ __forceinline__ void tmem_ld16x256_x2(unsigned taddr, unsigned* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16x256_x4(unsigned taddr, unsigned* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void a64_store2(unsigned char* a, int row, int col, unsigned v) {   // two bf16 at (row, col), col even
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(s32(a + (col >> 3) * CHUNK_A64 + row * 16 + (col & 7) * 2)), "r"(v) : "memory");
+}
+__device__ __forceinline__ SoftPart soft_merge(SoftPart a, SoftPart b) {
+  const float m = fmaxf(a.m, b.m);
+  const float sa = ex2f((a.m - m) * 1.4426950408889634f), sb = ex2f((b.m - m) * 1.4426950408889634f);
+  return SoftPart{m, a.z * sa + b.z * sb, a.y * sa + b.y * sb};
+}
+__device__ __forceinline__ SoftPart soft_quad(SoftPart p) {    // merge over the 4 lanes that share a row
+#pragma unroll
+  for (int off = 1; off <= 2; off <<= 1) {
+    SoftPart o{__shfl_xor_sync(0xffffffffu, p.m, off), __shfl_xor_sync(0xffffffffu, p.z, off), __shfl_xor_sync(0xffffffffu, p.y, off)};
+    p = soft_merge(p, o);
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(NPIPE, 1)
+k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem64& sm = *reinterpret_cast<Smem64*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer_warp = warp == NEPI / 32;
+  const int q = warp & 3;                  // TMEM lane quarter: tile rows 16q .. 16q+15
+  const int cb = (warp >> 2) & 3;          // head layers: 32-column block; hidden layers: 16-column slice of a round
+  const int rA = 16 * q + (lane >> 2), rB = rA + 8;     // the two tile rows of this thread's fragment
+  const int cq = 2 * (lane & 3);           // column offset inside an 8-column group
+
+  int tile = blockIdx.x;
+  const int T = (job.n_rows + TM64 - 1) / TM64;
+  const int branch = tile >= T;
+  tile -= branch * T;
+  const Chain& ch = branch ? chain1 : chain0;
+  const int nl = ch.n_layers;
+
+  auto load_weights = [&](int l) {
+    const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[l & 1], bytes);
+    bulk_g2s(sm.w[l & 1], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
+  };
+  if (tid == 0) {
+    mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
+    mbar_init(&sm.dbar[0], 1); mbar_init(&sm.dbar[1], 1);
+    mbar_init(&sm.bbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bbytes = (unsigned)nl * TN * 4;
+    mbar_expect_tx(&sm.bbar, bbytes);
+    bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
+    load_weights(0);
+    if (nl > 1) load_weights(1);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(2 * TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  smz_pdl_wait();
+  smz_pdl_launch_dependents();
+  // gather: epilogue thread i stages the 16-byte K-chunk (i >> 6) of tile row (i & 63); requested before the count
+  const int srow = tid & 63, skc = (tid >> 6) & 7;
+  int4 rec = make_int4(0, 0, 0, 0);
+  uint4 hrow = make_uint4(0, 0, 0, 0);
+  if (!is_issuer_warp) {
+    rec = a.rows4[smz_row_index(a, sim, branch, min(tile * TM64 + srow, a.B - 1))];
+    rec.x = min(max(rec.x, 0), a.B - 1);
+    rec.y = min(max(rec.y, 0), a.N);
+    hrow = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + rec.x) * SMZ_SP +
+                                           skc * 8);
+  }
+  const int count = a.branch_count[sim * 2 + branch];
+  if (tile * TM64 >= count) {
+    if (tid == 0) {
+      mbar_wait(&sm.bbar, 0);
+      mbar_wait(&sm.wbar[0], 0);
+      if (nl > 1) mbar_wait(&sm.wbar[1], 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(2 * TN) : "memory");
+    return;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = sm.tmem_base;
+
+  if (is_issuer_warp) {
+    const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A64, 128);
+    for (int l = 0; l < nl; ++l) {
+      const int nk = ch.layer[l].K / 16;
+      mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
+      const unsigned long long bd = umma_desc(s32(sm.w[l & 1]), CHUNK_W, 128);
+      const unsigned d = tmem + (unsigned)((l & 1) * TN);
+      for (int c = 0; c < 2; ++c) {
+        nb_sync(2 + c);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 4 * c; k < 4 * (c + 1); ++k)
+            if (k < nk)
+              umma64(d, ad + (unsigned long long)(k * ((2 * CHUNK_A64) >> 4)), bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)),
+                     k > 0 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(&sm.dbar[l & 1]);
+      __syncwarp();
+      if (l + 2 < nl) {
+        mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
+        if (lane == 0) load_weights(l + 2);
+        __syncwarp();
+      }
+    }
+  } else {
+    {   // stage the first A operand
+      const bool valid = tile * TM64 + srow < count;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(sm.a + skc * CHUNK_A64 + srow * 16)), "r"(valid ? hrow.x : 0u),
+                   "r"(valid ? hrow.y : 0u), "r"(valid ? hrow.z : 0u), "r"(valid ? hrow.w : 0u)
+                   : "memory");
+      if (skc < ch.onehot_pad / 8) {
+        const int act = valid ? rec.z : -1;
+        unsigned w4[4] = {0, 0, 0, 0};
+        if (act >= skc * 8 && act < skc * 8 + 8) {
+          const int j = act - skc * 8;
+          w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(sm.a + (8 + skc) * CHUNK_A64 + srow * 16)), "r"(w4[0]),
+                     "r"(w4[1]), "r"(w4[2]), "r"(w4[3])
+                     : "memory");
+      }
+      if (skc == 0) sm.rowidx[srow] = valid ? rec.x : -1;
+    }
+    fence_async_smem();
+    for (int c = 0; c < 2; ++c) nb_arrive(2 + c);
+    mbar_wait(&sm.bbar, 0);
+    epi_sync();                              // rowidx is read by other threads from here on
+    const unsigned lane_t = tmem + ((unsigned)(q * 32) << 16);
+    const int S = job.S;
+    const int idxA = sm.rowidx[rA], idxB = sm.rowidx[rB];
+
+    for (int l = 0; l < nl; ++l) {
+      const int kind = ch.layer[l].kind;
+      const unsigned dcol = (unsigned)((l & 1) * TN);
+      mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      if (kind == LK_HIDDEN) {
+        // two rounds of 64 columns; this warp owns columns 64c + 16cb .. +15 of round c for its 16 rows
+        unsigned raw[2][8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tmem_ld16x256_x2(lane_t + dcol + c * 64 + cb * 16, raw[c]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int col = c * 64 + cb * 16 + g * 8 + cq;
+            const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + col);
+            const float a0 = elu_fast(__uint_as_float(raw[c][4 * g + 0]) + bi.x), a1 = elu_fast(__uint_as_float(raw[c][4 * g + 1]) + bi.y);
+            const float b0 = elu_fast(__uint_as_float(raw[c][4 * g + 2]) + bi.x), b1 = elu_fast(__uint_as_float(raw[c][4 * g + 3]) + bi.y);
+            a64_store2(sm.a, rA, col, pack_bf16(a0, a1));
+            a64_store2(sm.a, rB, col, pack_bf16(b0, b1));
+          }
+          fence_async_smem();
+          if (c == 1) tc_fence_before();
+          nb_arrive(2 + c);
+        }
+      } else {
+        // head layer: this warp owns the 32-column block cb of its 16 rows (fragment: 4 groups x {rowA, rowB} x 2 columns)
+        const int c0 = cb * 32;
+        unsigned raw[16];
+        tmem_ld16x256_x4(lane_t + dcol + c0, raw);
+        tmem_wait_ld();
+        float xa[8], xb[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + c0 + g * 8 + cq);
+          xa[2 * g] = __uint_as_float(raw[4 * g + 0]) + bi.x; xa[2 * g + 1] = __uint_as_float(raw[4 * g + 1]) + bi.y;
+          xb[2 * g] = __uint_as_float(raw[4 * g + 2]) + bi.x; xb[2 * g + 1] = __uint_as_float(raw[4 * g + 3]) + bi.y;
+        }
+        const bool state_seg = (kind == LK_STATE || kind == LK_STATE_REWARD) && cb < 2;
+        const bool soft_seg = (kind == LK_STATE_REWARD && cb >= 2) || (kind == LK_PRED && cb < 2);
+        SoftPart spa{-1e30f, 0.f, 0.f}, spb{-1e30f, 0.f, 0.f};
+        if (state_seg) {
+          float loa = INFINITY, hia = -INFINITY, lob = INFINITY, hib = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            loa = fminf(loa, xa[i]); hia = fmaxf(hia, xa[i]);
+            lob = fminf(lob, xb[i]); hib = fmaxf(hib, xb[i]);
+          }
+#pragma unroll
+          for (int off = 1; off <= 2; off <<= 1) {
+            loa = fminf(loa, __shfl_xor_sync(0xffffffffu, loa, off)); hia = fmaxf(hia, __shfl_xor_sync(0xffffffffu, hia, off));
+            lob = fminf(lob, __shfl_xor_sync(0xffffffffu, lob, off)); hib = fmaxf(hib, __shfl_xor_sync(0xffffffffu, hib, off));
+          }
+          if ((lane & 3) == 0) {
+            sm.part[cb][rA] = make_float4(loa, hia, 0.f, 0.f);
+            sm.part[cb][rB] = make_float4(lob, hib, 0.f, 0.f);
+          }
+        } else if (soft_seg) {
+          float ma = -1e30f, mb = -1e30f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ma = fmaxf(ma, xa[i]); mb = fmaxf(mb, xb[i]); }
+          spa.m = ma; spb.m = mb;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float pos = (float)(((c0 + g * 8 + cq + j) & 63) - S / 2);
+              const float ea = ex2f((xa[2 * g + j] - ma) * 1.4426950408889634f), eb = ex2f((xb[2 * g + j] - mb) * 1.4426950408889634f);
+              spa.z += ea; spa.y = fmaf(pos, ea, spa.y);
+              spb.z += eb; spb.y = fmaf(pos, eb, spb.y);
+            }
+          spa = soft_quad(spa); spb = soft_quad(spb);
+          if ((lane & 3) == 0) {
+            sm.part[cb][rA] = make_float4(spa.m, spa.z, spa.y, 0.f);
+            sm.part[cb][rB] = make_float4(spb.m, spb.z, spb.y, 0.f);
+          }
+        }
+        epi_sync();
+        unsigned pend_a[4], pend_b[4];
+        bool have_pend = false;
+        if (state_seg) {
+          const float4 oa = sm.part[cb ^ 1][rA], ob = sm.part[cb ^ 1][rB], ma4 = sm.part[cb][rA], mb4 = sm.part[cb][rB];
+          const float loa = fminf(ma4.x, oa.x), hia = fmaxf(ma4.y, oa.y), lob = fminf(mb4.x, ob.x), hib = fmaxf(mb4.y, ob.y);
+          float sa = hia - loa, sb = hib - lob;
+          if (sa < 1e-5f) sa += 1e-5f;
+          if (sb < 1e-5f) sb += 1e-5f;
+          const float ia = 1.f / sa, ib = 1.f / sb;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            pend_a[g] = pack_bf16((xa[2 * g] - loa) * ia, (xa[2 * g + 1] - loa) * ia);
+            pend_b[g] = pack_bf16((xb[2 * g] - lob) * ib, (xb[2 * g + 1] - lob) * ib);
+            a64_store2(sm.a, rA, c0 + g * 8 + cq, pend_a[g]);
+            a64_store2(sm.a, rB, c0 + g * 8 + cq, pend_b[g]);
+          }
+          have_pend = job.hidden16_dst != nullptr;
+        } else if (soft_seg && (cb & 1) == 0) {
+          if ((lane & 3) == 0) {
+            const float4 oa = sm.part[cb + 1][rA], ob = sm.part[cb + 1][rB];
+            float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
+            if (dst) {
+              if (idxA >= 0) dst[idxA] = support_scalar(spa, SoftPart{oa.x, oa.y, oa.z});
+              if (idxB >= 0) dst[idxB] = support_scalar(spb, SoftPart{ob.x, ob.y, ob.z});
+            }
+          }
+        } else if (kind == LK_PRED && cb == 2) {
+          const int n = ch.n_policy;
+          float ma = -1e30f, mb = -1e30f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ma = fmaxf(ma, xa[i]); mb = fmaxf(mb, xb[i]); }
+#pragma unroll
+          for (int off = 1; off <= 2; off <<= 1) {
+            ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, off));
+          }
+          float za = 0.f, zb = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            xa[i] = ex2f((xa[i] - ma) * 1.4426950408889634f); za += xa[i];
+            xb[i] = ex2f((xb[i] - mb) * 1.4426950408889634f); zb += xb[i];
+          }
+#pragma unroll
+          for (int off = 1; off <= 2; off <<= 1) {
+            za += __shfl_xor_sync(0xffffffffu, za, off);
+            zb += __shfl_xor_sync(0xffffffffu, zb, off);
+          }
+          if (job.policy_dst) {
+            const float ia = 1.f / za, ib = 1.f / zb;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int i = g * 8 + cq + j;
+                if (i < n) {
+                  if (idxA >= 0) job.policy_dst[(size_t)idxA * job.pstride + i] = xa[2 * g + j] * ia;
+                  if (idxB >= 0) job.policy_dst[(size_t)idxB * job.pstride + i] = xb[2 * g + j] * ib;
+                }
+              }
+          }
+        }
+        if (l + 1 < nl) {
+          fence_async_smem();
+          tc_fence_before();
+          for (int c = 0; c < 2; ++c) nb_arrive(2 + c);
+        }
+        if (have_pend) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (idxA >= 0) *reinterpret_cast<unsigned*>(job.hidden16_dst + (size_t)idxA * SMZ_SP + c0 + g * 8 + cq) = pend_a[g];
+            if (idxB >= 0) *reinterpret_cast<unsigned*>(job.hidden16_dst + (size_t)idxB * SMZ_SP + c0 + g * 8 + cq) = pend_b[g];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The whole search loop of 128 trees in ONE persistent CTA (no inter-CTA dependency exists in the search:
 // trees are independent, so nothing but this tile's own progress gates the next simulation).
 // Per simulation: [expansion + backup of the previous one, descent of this one] on 4 lanes per tree ->
@@ -1171,6 +1525,8 @@ struct SmzBf16Image {
   int smem_bytes;
   long long* timeline;    // device debug buffer or null (SMZ_BF16_TIMELINE=1)
   int pipe_rounds;        // 2 (default) or 4 rounds per hidden layer in the pipelined kernel (SMZ_PIPE_ROUNDS)
+  int use_m64;            // 64-row tiles: -1 = by batch size (busy CTAs fit one wave of SMs), SMZ_M64=0/1 forces
+  int n_sms;
   int timeline_mega;
   int use_pipe;           // K-pipelined chain for the simulation step (SMZ_NO_PIPE=1 turns it off)
 };
@@ -1220,6 +1576,13 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   im->use_pipe = getenv("SMZ_NO_PIPE") ? 0 : 1;
+  im->use_m64 = getenv("SMZ_M64") ? atoi(getenv("SMZ_M64")) : -1;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&im->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || im->n_sms <= 0) im->n_sms = 148;
+  }
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
   im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
@@ -1356,6 +1719,14 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   job.timeline = im->timeline;
   const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
+  // 64-row tiles halve the MUFU-bound epilogue per SM as long as the busy CTAs (~trees / 64 + 2) fit one wave
+  // (measured on B200, cfg-2 shapes: 8192 trees 267 vs 240 M sims/s, 16384 trees 288 vs 350)
+  const bool m64 = im->use_m64 < 0 ? (n_trees + TM64 - 1) / TM64 + 2 <= im->n_sms : im->use_m64 != 0;
+  if (tree_mode == 0 && im->use_pipe && m64) {
+    const dim3 grid64(2 * ((n_trees + TM64 - 1) / TM64));
+    smz_launch(k_bf16_chain_m64, grid64, dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    return;
+  }
   if (tree_mode == 0 && im->use_pipe) {
     auto* kp = im->pipe_rounds == 4 ? k_bf16_chain_pipe<4> : k_bf16_chain_pipe<2>;
     smz_launch(kp, grid, dim3(NPIPE), sizeof(SmemPipe) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
