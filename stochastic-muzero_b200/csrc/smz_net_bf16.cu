@@ -140,6 +140,17 @@ __device__ __forceinline__ void umma(unsigned tmem_d, unsigned long long adesc, 
       "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
       : "memory");
 }
+// one lane of a converged warp, chosen by the hardware (elect.sync): ptxas keeps operands of the elected region in
+// uniform registers instead of wrapping every tcgen05.mma into an ELECT / R2UR.BROADCAST loop
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
@@ -666,9 +677,9 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         // the A columns of round c of this layer are in shared memory.  Every barrier is consumed for every layer
         // (also for column blocks a short-K layer does not read): arrivals and waits stay paired.
         nb_sync(2 + c);
-        if (tl && c == 0) tl[1 + l * 4 + 0] = clock64();
+        if (tl && c == NR - 1) tl[1 + l * 4 + 0] = clock64();   // last round of the layer is in the A operand
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = (8 / NR) * c; k < (8 / NR) * (c + 1); ++k)
             if (k < nk)
@@ -868,6 +879,12 @@ __device__ __forceinline__ void tmem_ld16x256_x2(unsigned taddr, unsigned* r) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16x256_x1(unsigned taddr, unsigned* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16x256_x4(unsigned taddr, unsigned* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -893,6 +910,8 @@ __device__ __forceinline__ SoftPart soft_quad(SoftPart p) {    // merge over the
   return p;
 }
 
+// R0 = columns of the first hidden-layer round (64: two even rounds; 96: 96 + 32, two K-steps left for the tail)
+template <int R0>
 __global__ void __launch_bounds__(NPIPE, 1)
 k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
@@ -910,6 +929,8 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   tile -= branch * T;
   const Chain& ch = branch ? chain1 : chain0;
   const int nl = ch.n_layers;
+  long long* tl = (job.timeline && blockIdx.x == 0 && lane == 0) ? job.timeline : nullptr;   // debug stamps
+  if (tl && tid == 0) tl[0] = clock64();
 
   auto load_weights = [&](int l) {
     const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
@@ -935,6 +956,7 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   }
   smz_pdl_wait();
   smz_pdl_launch_dependents();
+  if (tl && tid == 0) tl[1 + 4 * MAXL] = clock64();
   // gather: epilogue thread i stages the 16-byte K-chunk (i >> 6) of tile row (i & 63); requested before the count
   const int srow = tid & 63, skc = (tid >> 6) & 7;
   int4 rec = make_int4(0, 0, 0, 0);
@@ -974,17 +996,19 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
       for (int c = 0; c < 2; ++c) {
         nb_sync(2 + c);
+        if (tl && c == 1) tl[1 + l * 4 + 0] = clock64();       // last round of the layer is in the A operand
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 4 * c; k < 4 * (c + 1); ++k)
-            if (k < nk)
+          for (int k = 0; k < 8; ++k)
+            if (k >= (c ? R0 / 16 : 0) && k < (c ? 8 : R0 / 16) && k < nk)
               umma64(d, ad + (unsigned long long)(k * ((2 * CHUNK_A64) >> 4)), bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)),
                      k > 0 ? 1u : 0u);
         }
         __syncwarp();
       }
       if (lane == 0) umma_commit(&sm.dbar[l & 1]);
+      if (tl) tl[1 + l * 4 + 1] = clock64();
       __syncwarp();
       if (l + 2 < nl) {
         mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
@@ -1023,22 +1047,31 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       const int kind = ch.layer[l].kind;
       const unsigned dcol = (unsigned)((l & 1) * TN);
       mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
+      if (tl && warp == 0) tl[1 + l * 4 + 2] = clock64();
       __syncwarp();
       tc_fence_after();
       if (kind == LK_HIDDEN) {
-        // two rounds of 64 columns; this warp owns columns 64c + 16cb .. +15 of round c for its 16 rows
-        unsigned raw[2][8];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tmem_ld16x256_x2(lane_t + dcol + c * 64 + cb * 16, raw[c]);
+        // two rounds: columns [0, R0) and [R0, 128); this warp owns a quarter of each round for its 16 rows
+        constexpr int G0 = R0 / 32, G1 = (TN - R0) / 32;          // 8-column groups per warp in round 0 / 1
+        unsigned raw[4 * (G0 + G1)];
+        if constexpr (R0 == 64) {
+          tmem_ld16x256_x2(lane_t + dcol + cb * 16, raw);
+          tmem_ld16x256_x2(lane_t + dcol + 64 + cb * 16, raw + 8);
+        } else {
+          tmem_ld16x256_x2(lane_t + dcol + cb * 24, raw);
+          tmem_ld16x256_x1(lane_t + dcol + cb * 24 + 16, raw + 8);
+          tmem_ld16x256_x1(lane_t + dcol + 96 + cb * 8, raw + 12);
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = c * 64 + cb * 16 + g * 8 + cq;
+          for (int g = 0; g < (c ? G1 : G0); ++g) {
+            const int col = (c ? R0 + cb * 8 * G1 : cb * 8 * G0) + g * 8 + cq;
+            const unsigned* rr = raw + 4 * ((c ? G0 : 0) + g);
             const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + col);
-            const float a0 = elu_fast(__uint_as_float(raw[c][4 * g + 0]) + bi.x), a1 = elu_fast(__uint_as_float(raw[c][4 * g + 1]) + bi.y);
-            const float b0 = elu_fast(__uint_as_float(raw[c][4 * g + 2]) + bi.x), b1 = elu_fast(__uint_as_float(raw[c][4 * g + 3]) + bi.y);
+            const float a0 = elu_fast(__uint_as_float(rr[0]) + bi.x), a1 = elu_fast(__uint_as_float(rr[1]) + bi.y);
+            const float b0 = elu_fast(__uint_as_float(rr[2]) + bi.x), b1 = elu_fast(__uint_as_float(rr[3]) + bi.y);
             a64_store2(sm.a, rA, col, pack_bf16(a0, a1));
             a64_store2(sm.a, rB, col, pack_bf16(b0, b1));
           }
@@ -1173,6 +1206,7 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           }
         }
       }
+      if (tl && warp == 0) tl[1 + l * 4 + 3] = clock64();
     }
   }
   tc_fence_before();
@@ -1582,7 +1616,8 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&im->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || im->n_sms <= 0) im->n_sms = 148;
   }
-  cudaFuncSetAttribute((const void*)k_bf16_chain_m64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
   im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
@@ -1602,13 +1637,16 @@ void smz_bf16_destroy(SmzBf16Image* im) {
     if (cudaMemcpy(t, im->timeline, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "smz bf16 timeline (cycles, CTA 0 of the last simulation step):\n");
       for (int l = 0; l < MAXL && t[1 + l * 4 + 3]; ++l)
-        fprintf(stderr, "  layer %2d: start +%6lld | mma issue %5lld | issue->done (all threads) %5lld | epilogue+sync %5lld\n", l,
+        fprintf(stderr, "  layer %2d: A operand complete +%6lld | mma issue -> commit %5lld | commit -> accumulator seen %5lld | epilogue %5lld\n", l,
                 t[1 + l * 4] - t[0], t[1 + l * 4 + 1] - t[1 + l * 4], t[1 + l * 4 + 2] - t[1 + l * 4 + 1],
                 t[1 + l * 4 + 3] - t[1 + l * 4 + 2]);
       const long long* h = t + 1 + 4 * MAXL;
       if (im->timeline_mega)
         fprintf(stderr, "  persistent kernel, last simulation: tree phase %lld | barrier %lld | sort+gather %lld | to first layer +%lld\n",
                 h[0] - t[0], h[1] - h[0], h[2] - h[1], t[1] - h[2]);
+      else if (h[0] && !h[1])
+        fprintf(stderr, "  pipelined kernel: dependency wait returned at +%lld (A operand of layer 0 complete %lld cycles later)\n",
+                h[0] - t[0], t[1] - h[0]);
       else
       for (int k = 0; k < 2; ++k, h += 8)
         fprintf(stderr, "  %s head (thread 0): load+bias -> partials %lld | barrier %lld | finish %lld | fence+barrier %lld\n",
@@ -1724,7 +1762,9 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   const bool m64 = im->use_m64 < 0 ? (n_trees + TM64 - 1) / TM64 + 2 <= im->n_sms : im->use_m64 != 0;
   if (tree_mode == 0 && im->use_pipe && m64) {
     const dim3 grid64(2 * ((n_trees + TM64 - 1) / TM64));
-    smz_launch(k_bf16_chain_m64, grid64, dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    static const bool uneven = getenv("SMZ_M64_EVEN") == nullptr;     // 96 + 32 columns measured 2.7 % faster than 64 + 64
+    auto* k64 = uneven ? k_bf16_chain_m64<96> : k_bf16_chain_m64<64>;
+    smz_launch(k64, grid64, dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
     return;
   }
   if (tree_mode == 0 && im->use_pipe) {
