@@ -295,7 +295,7 @@ def main():
     depth = stats["mean_leaf_depth"]
     tb = tree_bytes_per_sim(depth, min(wl["K"], max(A, C)), 147 if vision else dims["state_dim"]) * B
     achieved_gbs = tb / ((t_sel + t_exp) * 1e-3) / 1e9
-    kname = {"bf16": "k_bf16_chain_pipe, tcgen05 bf16", "fp32": "k_net_sim, fp32 CUDA cores",
+    kname = {"bf16": "k_bf16_chain_m64 / k_bf16_chain_pipe, tcgen05 bf16", "fp32": "k_net_sim, fp32 CUDA cores",
              "vision": "k_vision_step, fp32 CUDA cores"}[net]
     roofline = {"kernel": "network step (%s)" % kname, "bound": "tensor", "achieved": achieved_tf,
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
