@@ -1762,7 +1762,7 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   const bool m64 = im->use_m64 < 0 ? (n_trees + TM64 - 1) / TM64 + 2 <= im->n_sms : im->use_m64 != 0;
   if (tree_mode == 0 && im->use_pipe && m64) {
     const dim3 grid64(2 * ((n_trees + TM64 - 1) / TM64));
-    static const bool uneven = getenv("SMZ_M64_EVEN") == nullptr;     // 96 + 32 columns measured 2.7 % faster than 64 + 64
+    const bool uneven = getenv("SMZ_M64_EVEN") == nullptr;     // 96 + 32 columns measured 2.7 % faster than 64 + 64
     auto* k64 = uneven ? k_bf16_chain_m64<96> : k_bf16_chain_m64<64>;
     smz_launch(k64, grid64, dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
     return;

@@ -325,7 +325,7 @@ static size_t mirror_bytes(const SmzArena& a, int lanes) {
 }
 
 bool smz_tree_mirror_fits(const SmzArena& a, int lanes) {
-  static const bool off = getenv("SMZ_NO_TREE_SMEM") != nullptr;
+  const bool off = getenv("SMZ_NO_TREE_SMEM") != nullptr;     // read per launch (launches are graph-captured): tests toggle it
   return !off && mirror_bytes(a, lanes) <= 96 * 1024;
 }
 

@@ -740,3 +740,44 @@ def test_api_misuse_is_reported_not_executed():
     with pytest.raises(ValueError, match="lanes_per_tree"):
         SearchEngine(search, A, C, max_trees=8, net="external", lanes_per_tree=3)
     eng.close(); ext.close()
+
+
+_VARIANTS = {
+    "chain_one_thread_issue": {"SMZ_NO_PIPE": "1"},
+    "chain_128_rows_2_rounds": {"SMZ_M64": "0"},
+    "chain_128_rows_4_rounds": {"SMZ_M64": "0", "SMZ_PIPE_ROUNDS": "4"},
+    "chain_64_rows_even_rounds": {"SMZ_M64": "1", "SMZ_M64_EVEN": "1"},
+    "tree_arena_only": {"SMZ_NO_TREE_SMEM": "1"},
+}
+
+
+def _bf16_search_record(monkeypatch, env, B=300, N=50):
+    for k in ("SMZ_NO_PIPE", "SMZ_M64", "SMZ_PIPE_ROUNDS", "SMZ_M64_EVEN", "SMZ_NO_TREE_SMEM"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    zn = golden_io.load_net_case("ckpt450")
+    eng = _net_engine(zn, B=B, N=N, net="bf16", rng="philox", seed=5, record=True)
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(11))
+    eng.root(obs=obs, train=True)
+    eng.simulate(N)
+    eng.stats()
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    roots = {k: v.cpu().numpy() for k, v in eng.read_roots().items()}
+    hid = eng.read_hidden(N).cpu().numpy()
+    eng.close()
+    return rec, roots, hid
+
+
+@pytest.mark.parametrize("variant", sorted(_VARIANTS))
+def test_kernel_variants_give_the_same_search(monkeypatch, variant):
+    """The shipped kernel choice (64-row pipelined chain + shared-memory tree step at this size) and every
+    fallback / large-batch variant run the same search: identical visit counts, hidden states and tree
+    statistics; network scalars identical up to the reduction order of the head layers."""
+    ref_rec, ref_roots, ref_hid = _bf16_search_record(monkeypatch, {})
+    rec, roots, hid = _bf16_search_record(monkeypatch, _VARIANTS[variant])
+    np.testing.assert_array_equal(roots["visits"], ref_roots["visits"])
+    np.testing.assert_array_equal(hid, ref_hid)
+    np.testing.assert_allclose(rec["sim_policy"], ref_rec["sim_policy"], atol=1e-6)
+    np.testing.assert_allclose(rec["sim_value"], ref_rec["sim_value"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(roots["root_values"], ref_roots["root_values"], rtol=1e-5, atol=1e-5)
