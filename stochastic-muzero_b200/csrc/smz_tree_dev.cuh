@@ -148,27 +148,37 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
   if (alive && g.gl == 0) path[0] = make_int4(0, ts.root.x, ts.root.y, 0);
   int L = 1, child = 0, child_key = 0;
   bool going = alive;
+  // the Dirichlet-mixed root priors are f64 and only used at depth 0: one load, before the loop
+  const double prior0 = (alive && g.gl < a.A) ? (srp ? srp[g.gl] : a.root_prior[(size_t)tree * a.A + g.gl]) : 0.0;
+  // Every group that is still descending is at depth == level, so the node kind (and the child count) is uniform
+  // across the warp: plain uniform branches instead of votes, loads and draws without divergent regions.
+  int level = 0;
   while (__any_sync(FULL, going)) {
     const bool act = going && g.gl < nch;
-    const bool chance = (depth >> 1) & 1;
-    int4 st = make_int4(0, 0, 0, 0);
-    int2 lk = make_int2(0, 0);
-    double prior0 = 0.0, pbc = 0.0;
-    if (act) {
-      if constexpr (MIRROR) {      // the tree's node records live in shared memory (k_backup_select_sm)
-        st = sst[cbase + g.gl];
-        lk = slk[cbase + g.gl];
-      } else {
-        st = a.stat[tb + cbase + g.gl];
-        lk = a.link[tb + cbase + g.gl];
-      }
-      if (depth == 0) prior0 = srp ? srp[g.gl] : a.root_prior[(size_t)tree * a.A + g.gl];
-      if (!chance) pbc = a.pbc[parent_visit];     // plain load: the table may live in shared memory
+    const bool chance = (level >> 1) & 1;
+    const int ci = act ? cbase + g.gl : 0;                     // idle lanes read node 0 and discard it
+    int4 st;
+    int2 lk;
+    if constexpr (MIRROR) {      // the tree's node records live in shared memory (k_backup_select_sm)
+      st = sst[ci];
+      lk = slk[ci];
+    } else {
+      st = a.stat[tb + ci];
+      lk = a.link[tb + ci];
     }
-    // the draw only depends on the cursor: it is computed while the loads are in flight
-    const double u = (going && (chance || act)) ? smz_rng_uniform(rng, tree, chance ? cursor : cursor + g.gl) : 0.0;
+    if (!act) { st = make_int4(0, 0, 0, 0); lk = make_int2(0, 0); }
+    const double pbc = chance ? 0.0 : a.pbc[going ? parent_visit : 0];     // plain load: the table may live in shared memory
+    // the draw only depends on the cursor; a window of draws may have been generated ahead (SmzRng::win)
+    const int uidx = chance ? cursor : cursor + g.gl;
+    const bool want = going && (chance || act);
+    const unsigned wofs = (unsigned)(uidx - rng.win_base);
+    const bool hit = rng.win != nullptr && wofs < (unsigned)rng.win_len;
+    double u = hit ? rng.win[wofs] : 0.0;
+    if (__any_sync(FULL, want && !hit)) {
+      if (want && !hit) u = smz_rng_uniform(rng, tree, uidx);
+    }
     int pick = 0;
-    if (__any_sync(FULL, going && chance)) {
+    if (chance) {
       // chance node: sample a child from the smoothed priors (mcts.py:249-255, T9)
       const float p = __int_as_float(st.w);
       const float om = act ? __fadd_rn(__fsub_rn(1.f, p), 1e-12f) : 0.f;
@@ -181,12 +191,12 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       pk = pk < nch ? pk : nch - 1;
       if (chance) { pick = pk; cursor += going ? 1 : 0; }
     }
-    if (__any_sync(FULL, going && !chance)) {
+    if (!chance) {
       // decision node: argmax of ucb_score, one fresh uniform per child (mcts.py:235-243, T3/T5/T6)
       double score = -__longlong_as_double(0x7ff0000000000000LL);
       int best = -1;
       if (act && !chance) {
-        const double prior = (depth == 0) ? prior0 : (double)__int_as_float(st.w);
+        const double prior = (level == 0) ? prior0 : (double)__int_as_float(st.w);
         // pbc = sqrt(n) * pb_c(n), the left-associated head of mcts.py:237, tabulated by the host
         const double ps = smz_div_r64(__dmul_rn(pbc, prior), (double)(st.x + 1), a.rcp64[st.x + 1]);
         double vs = 0.0;
@@ -226,6 +236,7 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
         ++depth;
       }
     }
+    ++level;
   }
   if (alive && g.gl == 0) {
     const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
