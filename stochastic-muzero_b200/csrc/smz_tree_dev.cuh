@@ -238,9 +238,34 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     }
     ++level;
   }
-  if (alive && g.gl == 0) {
-    const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
-    const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
+  // ---- leaf record.  The row compaction and the depth statistic are aggregated per warp: one atomic per branch
+  //      (and one for the depth sum) per warp instead of one per tree — thousands of same-address atomics per
+  //      simulation serialise in the L2 and their return value is on the critical path of the kernel.
+  const bool lead = alive && g.gl == 0;
+  const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
+  const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
+  int r = 0;
+  if (COMPACT) {
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const unsigned m = __ballot_sync(FULL, lead && branch == b);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(&a.branch_count[sim * 2 + b], __popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (lead && branch == b) r = base + __popc(m & ((1u << lane) - 1u));
+      }
+    }
+  }
+  {
+    int dsum = lead ? depth + 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
+    if ((threadIdx.x & 31u) == 0 && dsum) atomicAdd(a.depth_sum, (unsigned long long)dsum);
+  }
+  if (lead) {
     a.leaf_node[tree] = child;
     a.leaf_slot[tree] = slot;
     a.leaf_action[tree] = child_key;
@@ -251,11 +276,9 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     if (o_action) o_action[tree] = child_key;
     if (o_branch) o_branch[tree] = branch;
     if (COMPACT) {
-      const int r = atomicAdd(&a.branch_count[sim * 2 + branch], 1);
       a.rows[smz_row_index(a, sim, branch, r)] = tree;
       a.rows4[smz_row_index(a, sim, branch, r)] = make_int4(tree, slot, child_key, 0);
     }
-    atomicAdd(a.depth_sum, (unsigned long long)(depth + 1));
   }
 }
 
