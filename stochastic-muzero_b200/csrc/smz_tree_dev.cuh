@@ -128,7 +128,7 @@ struct TreeState {
 // while descending, so the backup needs ONE round trip (the record) instead of two (index -> stat).
 // COMPACT: append the tree to the per-branch row list of the simulation (one atomic per tree) for kernels that
 // re-tile the leaves by branch; the persistent per-tile kernel sorts its own rows instead.
-template <int G, bool COMPACT = true, bool MIRROR = false>
+template <int G, bool COMPACT = true, bool MIRROR = false, bool BLOCKAGG = false>
 __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& a, const SmzRng& rng, int tree, bool alive,
                                              int sim, TreeState ts, int* __restrict__ o_slot, int* __restrict__ o_action,
                                              int* __restrict__ o_branch, const int4* __restrict__ sst = nullptr,
@@ -247,15 +247,37 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
   int r = 0;
   if (COMPACT) {
     const unsigned lane = threadIdx.x & 31u;
+    if constexpr (BLOCKAGG) {
+      // whole-block kernels: warps reserve ranks in shared memory, two threads reserve the block's rows globally
+      __shared__ int s_cnt[2], s_base[2];
+      if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+      __syncthreads();
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const unsigned m = __ballot_sync(FULL, lead && branch == b);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        int base = 0;
-        if ((int)lane == leader) base = atomicAdd(&a.branch_count[sim * 2 + b], __popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        if (lead && branch == b) r = base + __popc(m & ((1u << lane) - 1u));
+      for (int b = 0; b < 2; ++b) {
+        const unsigned m = __ballot_sync(FULL, lead && branch == b);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if ((int)lane == leader) base = atomicAdd(&s_cnt[b], __popc(m));
+          base = __shfl_sync(FULL, base, leader);
+          if (lead && branch == b) r = base + __popc(m & ((1u << lane) - 1u));
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 2) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&a.branch_count[sim * 2 + threadIdx.x], s_cnt[threadIdx.x]) : 0;
+      __syncthreads();
+      r += s_base[branch];
+    } else {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const unsigned m = __ballot_sync(FULL, lead && branch == b);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if ((int)lane == leader) base = atomicAdd(&a.branch_count[sim * 2 + b], __popc(m));
+          base = __shfl_sync(FULL, base, leader);
+          if (lead && branch == b) r = base + __popc(m & ((1u << lane) - 1u));
+        }
       }
     }
   }
