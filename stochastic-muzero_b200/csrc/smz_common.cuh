@@ -95,7 +95,7 @@ inline cudaError_t smz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10, counter = (index>>1, stream, tree_lo, tree_hi), key = (seed_lo, seed_hi)
-// (restated on the CPU in oracle/mcts_oracle.py::philox_uniform and oracle/c/smz_oracle.c)
+// (restated on the CPU in oracle/mcts_oracle.py::philox_uniform)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 smz_philox(uint4 c, uint2 k) {
 #pragma unroll
