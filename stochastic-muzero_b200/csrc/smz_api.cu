@@ -164,6 +164,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.leaf_node, B); ALLOC(a.leaf_slot, B); ALLOC(a.leaf_action, B); ALLOC(a.leaf_branch, B);
   ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 4 * B); ALLOC(a.rows4, 4 * B); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
+  if (c.net_mode == SMZ_NET_BF16) { ALLOC(a.xin, 4 * B * 8); }
   if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8); }
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
@@ -207,6 +208,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if (rc == SMZ_OK && a.hidden) {
     cudaMemset(a.rows, 0, 4 * B * sizeof(int));          // speculative gathers read rows beyond the live count
     cudaMemset(a.rows4, 0, 4 * B * sizeof(int4));
+    if (a.xin) cudaMemset(a.xin, 0, 4 * B * 8 * sizeof(uint4));
     cudaError_t m = cudaMemset(a.hidden, 0, (size_t)(a.N + 1) * B * a.Sp * sizeof(float));
     if (m != cudaSuccess) rc = fail(SMZ_E_CUDA, "memset: %s", cudaGetErrorString(m));
   }

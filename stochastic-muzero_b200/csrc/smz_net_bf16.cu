@@ -638,12 +638,18 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   int4 rec = make_int4(0, 0, 0, 0);
   uint4 hrow[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
   if (!is_issuer_warp) {
-    rec = a.rows4[smz_row_index(a, sim, branch, min(tile * TM + r, a.B - 1))];
-    rec.x = min(max(rec.x, 0), a.B - 1);
-    rec.y = min(max(rec.y, 0), a.N);
-    const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + rec.x) * SMZ_SP;
+    const size_t ri = smz_row_index(a, sim, branch, min(tile * TM + r, a.B - 1));
+    rec = a.rows4[ri];
+    if (a.xin) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) hrow[q] = *reinterpret_cast<const uint4*>(src16 + (cb * 2 + q) * 8);
+      for (int q = 0; q < 2; ++q) hrow[q] = a.xin[ri * 8 + cb * 2 + q];   // copied by the descent: one dependent load less
+    } else {
+      rec.x = min(max(rec.x, 0), a.B - 1);
+      rec.y = min(max(rec.y, 0), a.N);
+      const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + rec.x) * SMZ_SP;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) hrow[q] = *reinterpret_cast<const uint4*>(src16 + (cb * 2 + q) * 8);
+    }
   }
   const int count = a.branch_count[sim * 2 + branch];
   if (tile * TM >= count) {        // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
@@ -962,11 +968,16 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   int4 rec = make_int4(0, 0, 0, 0);
   uint4 hrow = make_uint4(0, 0, 0, 0);
   if (!is_issuer_warp) {
-    rec = a.rows4[smz_row_index(a, sim, branch, min(tile * TM64 + srow, a.B - 1))];
-    rec.x = min(max(rec.x, 0), a.B - 1);
-    rec.y = min(max(rec.y, 0), a.N);
-    hrow = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec.y * a.B + rec.x) * SMZ_SP +
-                                           skc * 8);
+    const size_t ri = smz_row_index(a, sim, branch, min(tile * TM64 + srow, a.B - 1));
+    rec = a.rows4[ri];
+    if (a.xin) {
+      hrow = a.xin[ri * 8 + skc];              // the descent copied the parent's row: no dependent second load
+    } else {
+      rec.x = min(max(rec.x, 0), a.B - 1);
+      rec.y = min(max(rec.y, 0), a.N);
+      hrow = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.hidden) +
+                                             ((size_t)rec.y * a.B + rec.x) * SMZ_SP + skc * 8);
+    }
   }
   const int count = a.branch_count[sim * 2 + branch];
   if (tile * TM64 >= count) {

@@ -244,6 +244,17 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
   const bool lead = alive && g.gl == 0;
   const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
   const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
+  // the parent's hidden row is requested now and stored once the row index is known (bf16 network: a.xin)
+  uint4 hcopy[(G < 8) ? 8 / G : 1];
+  const bool copy_row = COMPACT && a.xin != nullptr && alive;
+  if (copy_row) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.hidden) + ((size_t)slot * a.B + tree) * 8;
+#pragma unroll
+    for (int j = 0; j < ((G < 8) ? 8 / G : 1); ++j) {
+      const int idx = g.gl + j * G;
+      hcopy[j] = idx < 8 ? src[idx] : make_uint4(0, 0, 0, 0);
+    }
+  }
   int r = 0;
   if (COMPACT) {
     const unsigned lane = threadIdx.x & 31u;
@@ -278,6 +289,17 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
           base = __shfl_sync(FULL, base, leader);
           if (lead && branch == b) r = base + __popc(m & ((1u << lane) - 1u));
         }
+      }
+    }
+  }
+  if (COMPACT) {
+    const int rg = g.bcast(r, 0);
+    if (copy_row) {
+      uint4* dst = a.xin + smz_row_index(a, sim, branch, rg) * 8;
+#pragma unroll
+      for (int j = 0; j < ((G < 8) ? 8 / G : 1); ++j) {
+        const int idx = g.gl + j * G;
+        if (idx < 8) dst[idx] = hcopy[j];
       }
     }
   }
