@@ -92,24 +92,30 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+        def collect(windowed):
+            sm, mx, reasons = [], [], set()
+            for line in out.strip().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
                     continue
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if windowed and t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                        continue
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sorted(sm), mx, reasons
+        sm, mx, reasons = collect(True)
+        window = "timed region"
+        if not sm:      # a very short timed region can fall between two 50 ms samples: use the whole run (warm-up included)
+            sm, mx, reasons = collect(False)
+            window = "whole run (timed region shorter than the sampling period)"
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def run_reference(args):
