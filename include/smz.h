@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMZ_ABI_VERSION 1
+#define SMZ_ABI_VERSION 2
 
 enum {
   SMZ_OK = 0,
@@ -41,6 +41,9 @@ enum {
   SMZ_NET_EXTERNAL = 0, /* caller supplies policy/value/reward (tape replay, host-model callback)   */
   SMZ_NET_FP32 = 1,     /* fused fp32 CUDA-core MLP step (parity mode, 1e-5 vs the reference)       */
   SMZ_NET_BF16 = 2,     /* fused bf16 tcgen05/TMEM MLP step, fp32 accumulate (throughput mode)      */
+  SMZ_NET_TC32 = 4,     /* fused tcgen05/TMEM MLP step at the reference's precision: every fp32 operand split into
+                         * fp16 hi + lo, three products per K-step into one fp32 accumulator (1e-5 vs the reference,
+                         * like SMZ_NET_FP32, at tensor-core speed); |activations| must stay below 65504            */
   SMZ_NET_VISION = 3    /* vision (ResNet-v2, neural_network_vision_model.py) family, fp32 CUDA cores:
                          * obs_dim must be 3*98*98 (the reference fixes the model input, muzero_model.py:336),
                          * hidden state 3x7x7, state_dim/hidden_dim/num_hidden_layers = S/H/L of the MLP
@@ -111,7 +114,7 @@ typedef struct smz_tree_host {
   double* root_prior;  /* A entries: float64 priors of the root children (after Dirichlet mixing) */
   float minmax[2];     /* MinMaxStats.minimum / .maximum */
   int32_t n_uniforms;  /* uniform draws consumed so far */
-  int32_t root_to_play;
+  int32_t root_to_play; /* as stored: root_to_play_dev[tree] wrapped into [0, n_phases) */
 } smz_tree_host;
 
 int smz_create(const smz_config* cfg, smz_engine** out);
@@ -148,7 +151,8 @@ int smz_set_uniform_tape(smz_engine* e, const double* uniforms_dev, int32_t stri
 
 /* Root step (monte_carlo_tree_search.py:315-323).  Either obs_dev (float[n_trees][obs_dim], internal
  * network: representation + prediction) or root_policy_dev (float[n_trees][policy_stride], softmaxed,
- * external network) must be given.  root_to_play_dev: int32[n_trees] or NULL (all 0).
+ * external network) must be given.  root_to_play_dev: int32[n_trees] or NULL (all 0); values are wrapped into
+ * [0, n_phases) like Player_cycle.global_step() does (monte_carlo_tree_search.py:55-58).
  * train != 0 mixes Dirichlet noise into the root priors (skipped when N == 0, :215-216);
  * dirichlet_dev: double[n_trees][A] recorded noise, or NULL to draw it on the device. */
 int smz_root(smz_engine* e, int32_t n_trees, const float* obs_dev, const float* root_policy_dev,
@@ -166,6 +170,10 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* leaf_parent_slot_dev, int32_
                int32_t* leaf_branch_dev, void* stream);
 /* internal network on the leaves chosen by the last smz_select */
 int smz_net_step(smz_engine* e, int32_t sim, void* stream);
+/* The tree step exactly as smz_simulate's captured loop runs it between two network steps: expansion + backup
+ * of simulation `sim` on the outputs of smz_net_step, fused with the descent of simulation `sim + 1`
+ * (sim + 1 < N).  Stand-alone launch (no programmatic dependency): bench.py times the real kernel with it. */
+int smz_backup_select(smz_engine* e, int32_t sim, void* stream);
 /* expansion + backup of simulation `sim` (:289-308).  With policy_dev == NULL the outputs of
  * smz_net_step are used; else policy_dev float[n_trees][policy_stride] (softmaxed), value_dev /
  * reward_dev float[n_trees]. */
@@ -185,9 +193,12 @@ int smz_net_eval(smz_engine* e, int32_t which, int32_t n_rows, const float* in_d
 
 /* Root statistics consumed by Game.store_search_statistics / policy_step (game.py:179-235):
  * visits int32[n][A], root_values float[n] (= Node.value() of the root), priors double[n][A],
- * rewards float[n][A].  Any pointer may be NULL. */
+ * rewards float[n][A]; error_dev int32[1] = the search's error flag (0 ok, 1 uniform tape exhausted,
+ * 2 NaN / all-zero policy met during an expansion — where np.random.choice raises in the reference,
+ * monte_carlo_tree_search.py:208/:294), delivered with the same read-out so that the host needs no extra
+ * synchronisation to learn about it.  Any pointer may be NULL. */
 int smz_read_roots(smz_engine* e, int32_t* visits_dev, float* root_values_dev, double* priors_dev,
-                   float* rewards_dev, void* stream);
+                   float* rewards_dev, int32_t* error_dev, void* stream);
 /* The step after the search (game.py:179-235), on the device so that B games advance without a host
  * round-trip: stored_policy double[n][A] = visit distribution (priors when fewer than 3 visits,
  * store_search_statistics); policy double[n][A] = visits (priors when <= 1 visit) ** (1/temperature) only
@@ -205,8 +216,10 @@ int smz_read_hidden(smz_engine* e, int32_t slot, float* out_dev, void* stream);
  * dirichlet double[n][A], root_policy float[n][policy_stride]. */
 int smz_read_record(smz_engine* e, float* policy_dev, float* value_dev, float* reward_dev,
                     int8_t* branch_dev, double* dirichlet_dev, float* root_policy_dev, void* stream);
-/* Mean leaf depth and kernel-launch count of the last smz_root+smz_simulate (bench bookkeeping). */
-int smz_stats(smz_engine* e, double* mean_leaf_depth, int64_t* launches, void* stream);
+/* Synchronises `stream`.  Mean leaf depth and kernel-launch count of the last smz_root + smz_simulate, and the
+ * number of kernels this engine has launched since smz_create (bench bookkeeping: `gpu_launches`).  Returns
+ * SMZ_E_CAPACITY / SMZ_E_STATE when the last search raised its error flag (see smz_read_roots). */
+int smz_stats(smz_engine* e, double* mean_leaf_depth, int64_t* launches, int64_t* launches_total, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,16 @@ import warnings
 
 import numpy as np
 
-REFERENCE_DIR = os.environ.get("SMZ_REFERENCE", "/root/reference")
+def _find_reference():
+    """$SMZ_REFERENCE, then a driver-provided copy under baseline/_ref, then the container's mount."""
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in (os.environ.get("SMZ_REFERENCE"), os.path.join(repo, "baseline", "_ref"), "/root/reference"):
+        if d and os.path.isfile(os.path.join(d, "monte_carlo_tree_search.py")):
+            return d
+    return os.environ.get("SMZ_REFERENCE", "/root/reference")
+
+
+REFERENCE_DIR = _find_reference()
 
 
 def available() -> bool:

@@ -6,9 +6,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmz.so")
 
-SMZ_ABI_VERSION = 1
+SMZ_ABI_VERSION = 2
 SMZ_OK, SMZ_E_INVALID_ARG, SMZ_E_CUDA, SMZ_E_CAPACITY, SMZ_E_STATE = 0, -1, -2, -3, -4
-NET_EXTERNAL, NET_FP32, NET_BF16, NET_VISION = 0, 1, 2, 3
+NET_EXTERNAL, NET_FP32, NET_BF16, NET_VISION, NET_TC32 = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_TAPE = 0, 1
 
 
@@ -62,12 +62,13 @@ SIGNATURES = {
     "smz_net_step": (C.c_int, [_P, C.c_int32, _P]),
     "smz_expand_backup": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "smz_net_eval": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "smz_read_roots": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "smz_backup_select": (C.c_int, [_P, C.c_int32, _P]),
+    "smz_read_roots": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "smz_select_actions": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "smz_export_tree": (C.c_int, [_P, C.c_int32, C.POINTER(smz_tree_host), _P]),
     "smz_read_hidden": (C.c_int, [_P, C.c_int32, _P, _P]),
     "smz_read_record": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
-    "smz_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),
+    "smz_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
 }
 
 _lib = None

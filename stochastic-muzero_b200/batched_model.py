@@ -17,6 +17,8 @@ vision models), softmax on the policy head (:837), inverse_transform_with_suppor
 """
 from __future__ import annotations
 
+import copy
+
 import torch
 
 
@@ -39,7 +41,9 @@ class ReferenceModuleBackend:
         for name in ("representation", "prediction", "afterstate_dynamics", "afterstate_prediction", "dynamics"):
             m = getattr(model, f"{name}_function")
             m = m.module if m.__class__.__name__ == "DataParallel" else m
-            mods[name] = m.to(self.device).float().eval()
+            # a private copy: the caller's modules keep their device, dtype and train/eval mode (the trainer still
+            # owns them); the search object rebuilds this back-end whenever weights_version(model) changes
+            mods[name] = copy.deepcopy(m).to(self.device).float().eval()
         self.m = mods
 
     def _onehot(self, idx, like):

@@ -13,6 +13,7 @@
 #include "../../include/smz.h"
 #include "smz_kernels.h"
 #include "smz_net_bf16.h"
+#include "smz_net_tc32.h"
 #include "smz_net_vision.h"
 
 static thread_local char g_err[512] = "";
@@ -24,6 +25,21 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+// Every entry point works on the engine's device and leaves the caller's current device as it found it
+// (torch allocations and launches of the calling thread follow the current device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(e_)                                                                                    \
+  DeviceGuard guard_((e_)->cfg.device);                                                                 \
+  if (guard_.err != cudaSuccess) return fail(SMZ_E_CUDA, "cudaSetDevice(%d) failed: %s", (e_)->cfg.device, cudaGetErrorString(guard_.err))
 
 #define CU(call)                                                                                  \
   do {                                                                                            \
@@ -40,6 +56,7 @@ struct smz_engine {
   float* img32_buf;
   float* blob_buf;
   SmzBf16Image* bf16;    // tcgen05 path state (null unless net_mode == SMZ_NET_BF16)
+  SmzTc32Image* tc32;    // fp32-grade tcgen05 path state (null unless net_mode == SMZ_NET_TC32)
   SmzVisionImage* vision;  // vision family state (null unless net_mode == SMZ_NET_VISION)
   double* pbc_dev;
   double* rcp64_dev;
@@ -51,7 +68,8 @@ struct smz_engine {
   int n_trees;           // trees of the current search
   int sims_done;
   int have_weights;
-  int64_t launches;
+  int64_t launches;        // kernels of the last smz_root + smz_simulate
+  int64_t launches_total;  // kernels since smz_create
   cudaGraphExec_t graph_exec;
   int graph_trees, graph_sims, graph_first;
   cudaStream_t capture_stream;
@@ -59,6 +77,8 @@ struct smz_engine {
 };
 
 const char* smz_last_error(void) { return g_err; }
+
+static void count_launches(smz_engine* e, int64_t n) { e->launches += n; e->launches_total += n; }
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -103,7 +123,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if (c.action_dim > SMZ_MAX_POLICY || c.chance_dim > SMZ_MAX_POLICY)
     return fail(SMZ_E_CAPACITY, "smz_create: policy width %d/%d exceeds %d (one lane per policy entry)",
                 c.action_dim, c.chance_dim, SMZ_MAX_POLICY);
-  if (c.net_mode < SMZ_NET_EXTERNAL || c.net_mode > SMZ_NET_VISION) return fail(SMZ_E_INVALID_ARG, "bad net_mode");
+  if (c.net_mode < SMZ_NET_EXTERNAL || c.net_mode > SMZ_NET_TC32) return fail(SMZ_E_INVALID_ARG, "bad net_mode");
   if (c.net_mode == SMZ_NET_VISION) {
     if (c.obs_dim != 3 * 98 * 98) return fail(SMZ_E_INVALID_ARG, "smz_create: vision models take 3x98x98 observations (obs_dim %d)", c.obs_dim);
     if (c.action_dim != c.chance_dim) return fail(SMZ_E_INVALID_ARG, "smz_create: vision family needs chance_dim == action_dim");
@@ -121,13 +141,14 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if ((lanes & (lanes - 1)) || lanes < need || lanes > 32)
     return fail(SMZ_E_INVALID_ARG, "smz_create: lanes_per_tree must be a power of two in [%d, 32]", need);
 
-  CU(cudaSetDevice(c.device));
+  DeviceGuard guard_(c.device);
+  if (guard_.err != cudaSuccess) return fail(SMZ_E_CUDA, "cudaSetDevice(%d) failed: %s", c.device, cudaGetErrorString(guard_.err));
   smz_engine* e = new smz_engine();
   e->cfg = c;
   memset(&e->dims, 0, sizeof(e->dims));
   memset(&e->a, 0, sizeof(e->a));
-  e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr; e->vision = nullptr;
-  e->n_trees = 0; e->sims_done = 0; e->have_weights = 0; e->launches = 0;
+  e->img32_buf = nullptr; e->blob_buf = nullptr; e->bf16 = nullptr; e->tc32 = nullptr; e->vision = nullptr;
+  e->n_trees = 0; e->sims_done = 0; e->have_weights = 0; e->launches = 0; e->launches_total = 0;
   e->use_pdl = getenv("SMZ_NO_PDL") ? 0 : 1;
   e->use_mega = getenv("SMZ_MEGA") ? 1 : 0;
   // measured on B200 (4096 trees): the single-launch variant is ~4 % SLOWER than network kernel + tree kernel —
@@ -164,7 +185,8 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.leaf_node, B); ALLOC(a.leaf_slot, B); ALLOC(a.leaf_action, B); ALLOC(a.leaf_branch, B);
   ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 4 * B); ALLOC(a.rows4, 4 * B); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
-  if (c.net_mode == SMZ_NET_BF16) { ALLOC(a.xin, 4 * B * 8); }
+  a.xin_q = c.net_mode == SMZ_NET_TC32 ? 16 : 8;
+  if (c.net_mode == SMZ_NET_BF16 || c.net_mode == SMZ_NET_TC32) { ALLOC(a.xin, 4 * B * a.xin_q); }
   if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8); }
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
@@ -208,11 +230,12 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if (rc == SMZ_OK && a.hidden) {
     cudaMemset(a.rows, 0, 4 * B * sizeof(int));          // speculative gathers read rows beyond the live count
     cudaMemset(a.rows4, 0, 4 * B * sizeof(int4));
-    if (a.xin) cudaMemset(a.xin, 0, 4 * B * 8 * sizeof(uint4));
+    if (a.xin) cudaMemset(a.xin, 0, 4 * B * a.xin_q * sizeof(uint4));
     cudaError_t m = cudaMemset(a.hidden, 0, (size_t)(a.N + 1) * B * a.Sp * sizeof(float));
     if (m != cudaSuccess) rc = fail(SMZ_E_CUDA, "memset: %s", cudaGetErrorString(m));
   }
   if (rc == SMZ_OK && c.net_mode == SMZ_NET_BF16) rc = smz_bf16_create(e->shape, a, &e->bf16, g_err, sizeof(g_err));
+  if (rc == SMZ_OK && c.net_mode == SMZ_NET_TC32) rc = smz_tc32_create(e->shape, &e->tc32, g_err, sizeof(g_err));
   if (rc == SMZ_OK && c.net_mode == SMZ_NET_VISION)
     rc = smz_vision_create(a.A, c.state_dim, c.hidden_dim, c.num_hidden_layers, &e->vision, g_err, sizeof(g_err));
   if (rc == SMZ_OK && cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -224,7 +247,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
 
 int smz_destroy(smz_engine* e) {
   if (!e) return SMZ_OK;
-  cudaSetDevice(e->cfg.device);
+  DeviceGuard guard_(e->cfg.device);
   if (e->a.dbg) {
     long long t[8];
     if (cudaMemcpy(t, e->a.dbg, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -234,6 +257,7 @@ int smz_destroy(smz_engine* e) {
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
   if (e->bf16) smz_bf16_destroy(e->bf16);
+  if (e->tc32) smz_tc32_destroy(e->tc32);
   if (e->vision) smz_vision_destroy(e->vision);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
@@ -254,14 +278,14 @@ static void drop_graph(smz_engine* e) {
 int smz_set_pbc_table(smz_engine* e, const double* t, int32_t n) {
   if (!e || !t) return fail(SMZ_E_INVALID_ARG, "smz_set_pbc_table: null argument");
   if (n != e->a.N + 2) return fail(SMZ_E_INVALID_ARG, "smz_set_pbc_table: need %d entries, got %d", e->a.N + 2, n);
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   CU(cudaMemcpy(e->pbc_dev, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
   return SMZ_OK;
 }
 
 int smz_set_player_tables(smz_engine* e, const int8_t* sign, const int32_t* to_play, int32_t n_phases) {
   if (!e || !sign || !to_play || n_phases < 1) return fail(SMZ_E_INVALID_ARG, "smz_set_player_tables: bad argument");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   const size_t n = (size_t)n_phases * (e->a.N + 2);
   signed char* d = nullptr;
   CU(dev_alloc(e, &d, n));
@@ -281,7 +305,7 @@ int smz_set_weights(smz_engine* e, const float* blob, uint64_t n_floats, int32_t
     return fail(SMZ_E_INVALID_ARG, "smz_set_weights: blob has %llu floats, model shape needs %llu",
                 (unsigned long long)n_floats, (unsigned long long)e->dims.weight_blob_floats);
   cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   CU(cudaMemcpyAsync(e->blob_buf, blob, n_floats * sizeof(float),
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   if (e->vision) {
@@ -295,6 +319,10 @@ int smz_set_weights(smz_engine* e, const float* blob, uint64_t n_floats, int32_t
     int rc = smz_bf16_pack(e->bf16, e->shape, e->blob_buf, s, g_err, sizeof(g_err));
     if (rc != SMZ_OK) return rc;
   }
+  if (e->tc32) {
+    int rc = smz_tc32_pack(e->tc32, e->shape, e->blob_buf, s, g_err, sizeof(g_err));
+    if (rc != SMZ_OK) return rc;
+  }
   CU(cudaGetLastError());
   e->have_weights = 1;
   return SMZ_OK;
@@ -302,7 +330,7 @@ int smz_set_weights(smz_engine* e, const float* blob, uint64_t n_floats, int32_t
 
 int smz_set_seed(smz_engine* e, uint64_t seed, uint64_t tree_id_offset, void* stream) {
   if (!e) return fail(SMZ_E_INVALID_ARG, "smz_set_seed: null engine");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   // stream-ordered 16-byte update through a kernel-free path: the values are baked into the memcpy node
   const unsigned long long st[2] = {seed, tree_id_offset};
   CU(cudaMemcpyAsync(e->seed_dev, st, sizeof(st), cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -331,7 +359,7 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   if (obs && !e->have_weights) return fail(SMZ_E_STATE, "smz_root: smz_set_weights has not been called");
   if (e->cfg.rng_mode == SMZ_RNG_TAPE && !e->a.tape_u) return fail(SMZ_E_STATE, "smz_root: no uniform tape set");
   cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   SmzArena& a = e->a;
   CU(cudaMemsetAsync(a.branch_count, 0, (size_t)(a.N + 1) * 2 * sizeof(int), s));
   CU(cudaMemsetAsync(a.error_flag, 0, sizeof(int), s));
@@ -340,10 +368,11 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   if (e->cfg.num_simulations == 0) train = 0;   // mcts.py:215-216
   const float* policy = root_policy;
   if (obs) {
-    if (e->vision) { smz_vision_root(e->vision, a, n_trees, obs, s); e->launches += 1; }
+    if (e->vision) { smz_vision_root(e->vision, a, n_trees, obs, s); count_launches(e, 1); }
     else if (e->bf16) smz_bf16_root(e->bf16, a, e->shape, n_trees, obs, s);
+    else if (e->tc32) smz_tc32_root(e->tc32, a, e->shape, n_trees, obs, s);
     else smz_net_f32_root(a, e->shape, e->img32, n_trees, obs, s);
-    e->launches += 1;
+    count_launches(e, 1);
     policy = a.out_policy;
   }
   if (train) {
@@ -351,11 +380,11 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
       CU(cudaMemcpyAsync(a.dirichlet, dirichlet, (size_t)n_trees * a.A * sizeof(double), cudaMemcpyDeviceToDevice, s));
     } else {
       smz_launch_dirichlet(a, n_trees, s);
-      e->launches += 1;
+      count_launches(e, 1);
     }
   }
   smz_launch_root_expand(a, e->cfg.lanes_per_tree, n_trees, policy, a.W, root_to_play, train, a.dirichlet, s);
-  e->launches += 1;
+  count_launches(e, 1);
   CU(cudaGetLastError());
   e->n_trees = n_trees;
   e->sims_done = 0;
@@ -372,9 +401,9 @@ static int check_sim(smz_engine* e, int sim, const char* who) {
 int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32_t* branch, void* stream) {
   int rc = check_sim(e, sim, "smz_select");
   if (rc) return rc;
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   smz_launch_select(e->a, e->cfg.lanes_per_tree, e->n_trees, sim, slot, action, branch, (cudaStream_t)stream);
-  e->launches += 1;
+  count_launches(e, 1);
   CU(cudaGetLastError());
   return SMZ_OK;
 }
@@ -382,6 +411,7 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32
 static void enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false, int tree_mode = 0) {
   if (e->vision) smz_vision_sim(e->vision, e->a, e->n_trees, sim, s);
   else if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, tree_mode, s);
+  else if (e->tc32) smz_tc32_sim(e->tc32, e->a, e->shape, e->n_trees, sim, pdl, s);
   else smz_net_f32_sim(e->a, e->shape, e->img32, e->n_trees, sim, s);
 }
 
@@ -390,9 +420,9 @@ int smz_net_step(smz_engine* e, int32_t sim, void* stream) {
   if (rc) return rc;
   if (e->cfg.net_mode == SMZ_NET_EXTERNAL) return fail(SMZ_E_STATE, "smz_net_step: engine has no internal network");
   if (!e->have_weights) return fail(SMZ_E_STATE, "smz_net_step: smz_set_weights has not been called");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   enqueue_net(e, sim, (cudaStream_t)stream);
-  e->launches += 1;
+  count_launches(e, 1);
   CU(cudaGetLastError());
   return SMZ_OK;
 }
@@ -402,11 +432,24 @@ int smz_expand_backup(smz_engine* e, int32_t sim, const float* policy, const flo
   int rc = check_sim(e, sim, "smz_expand_backup");
   if (rc) return rc;
   if (policy && (!value || !reward)) return fail(SMZ_E_INVALID_ARG, "smz_expand_backup: value/reward missing");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   const SmzArena& a = e->a;
   smz_launch_expand_backup(a, e->cfg.lanes_per_tree, e->n_trees, sim, policy ? policy : a.out_policy, a.W,
                            policy ? value : a.out_value, policy ? reward : a.out_reward, (cudaStream_t)stream);
-  e->launches += 1;
+  count_launches(e, 1);
+  if (sim + 1 > e->sims_done) e->sims_done = sim + 1;
+  CU(cudaGetLastError());
+  return SMZ_OK;
+}
+
+int smz_backup_select(smz_engine* e, int32_t sim, void* stream) {
+  int rc = check_sim(e, sim, "smz_backup_select");
+  if (rc) return rc;
+  if (sim + 1 >= e->a.N) return fail(SMZ_E_CAPACITY, "smz_backup_select: simulation %d has no successor (N = %d)", sim, e->a.N);
+  if (e->cfg.net_mode == SMZ_NET_EXTERNAL) return fail(SMZ_E_STATE, "smz_backup_select: engine has no internal network");
+  ON_DEVICE(e);
+  smz_launch_backup_select(e->a, e->cfg.lanes_per_tree, e->n_trees, sim, false, (cudaStream_t)stream);
+  count_launches(e, 1);
   if (sim + 1 > e->sims_done) e->sims_done = sim + 1;
   CU(cudaGetLastError());
   return SMZ_OK;
@@ -418,7 +461,7 @@ static void enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   // select(first); then per simulation: network step, then [expand+backup(sim) fused with select(sim+1)]
   // With the tensor-core network both hot kernels are chained by programmatic dependent launch: the
   // next kernel's CTAs become resident and run their prologue while the previous one drains.
-  const bool pdl = e->bf16 != nullptr && e->use_pdl;
+  const bool pdl = (e->bf16 != nullptr || e->tc32 != nullptr) && e->use_pdl;
   smz_launch_select(a, G, e->n_trees, first, nullptr, nullptr, nullptr, s);
   // tensor-core network + 4 lanes per tree: the tree phases run in the tail of the network kernel (one launch
   // per simulation); otherwise a second, fused tree kernel follows each network step
@@ -441,13 +484,13 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     return fail(SMZ_E_CAPACITY, "smz_simulate: %d + %d simulations exceed num_simulations %d", e->sims_done, n_sims, e->a.N);
   if (n_sims == 0) return SMZ_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   const int first = e->sims_done;
   if (e->use_mega && smz_bf16_mega_supported(e->bf16, e->a, e->cfg.lanes_per_tree)) {
     // tensor-core network + narrow policies: one persistent launch runs the whole loop, tile by tile
     smz_bf16_mega(e->bf16, e->a, e->shape, e->n_trees, first, n_sims, s);
     CU(cudaGetLastError());
-    e->launches += 1;
+    count_launches(e, 1);
     e->sims_done += n_sims;
     return SMZ_OK;
   }
@@ -463,7 +506,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
       ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
       cudaGraphDestroy(graph);
     }
-    if (ce != cudaSuccess && e->use_pdl && e->bf16) {
+    if (ce != cudaSuccess && e->use_pdl && (e->bf16 || e->tc32)) {
       // programmatic edges not capturable on this driver: fall back to plain stream order, once
       cudaGetLastError();
       e->graph_exec = nullptr;
@@ -474,7 +517,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     e->graph_trees = e->n_trees; e->graph_sims = n_sims; e->graph_first = first;
   }
   CU(cudaGraphLaunch(e->graph_exec, s));
-  e->launches += ((e->bf16 && e->cfg.lanes_per_tree == 4 && e->use_fused_tree) ? 1LL : 2LL) * n_sims + 1;
+  count_launches(e, ((e->bf16 && e->cfg.lanes_per_tree == 4 && e->use_fused_tree) ? 1LL : 2LL) * n_sims + 1);
   e->sims_done += n_sims;
   return SMZ_OK;
 }
@@ -486,7 +529,7 @@ int smz_net_eval(smz_engine* e, int32_t which, int32_t n_rows, const float* in, 
   if (!e->have_weights) return fail(SMZ_E_STATE, "smz_net_eval: smz_set_weights has not been called");
   if (which < 0 || which > 5 || n_rows < 1) return fail(SMZ_E_INVALID_ARG, "smz_net_eval: bad which / n_rows");
   if ((which == 2 || which == 4) && !idx) return fail(SMZ_E_INVALID_ARG, "smz_net_eval: idx_dev required");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   if (e->vision) {
     if (smz_vision_eval(e->vision, which, n_rows, in, idx, hidden_out, policy_out, value_out, reward_out, e->a.W,
                         (cudaStream_t)stream) != SMZ_OK)
@@ -497,6 +540,9 @@ int smz_net_eval(smz_engine* e, int32_t which, int32_t n_rows, const float* in, 
   if (e->bf16)
     smz_bf16_eval(e->bf16, e->shape, which, n_rows, in, idx, hidden_out, policy_out, value_out, reward_out, code_out,
                   e->a.W, (cudaStream_t)stream);
+  else if (e->tc32)
+    smz_tc32_eval(e->tc32, e->shape, which, n_rows, in, idx, hidden_out, policy_out, value_out, reward_out, code_out,
+                  e->a.W, (cudaStream_t)stream);
   else
     smz_net_f32_eval(e->shape, e->img32, which, n_rows, in, idx, hidden_out, policy_out, value_out, reward_out,
                      code_out, e->a.W, (cudaStream_t)stream);
@@ -504,12 +550,13 @@ int smz_net_eval(smz_engine* e, int32_t which, int32_t n_rows, const float* in, 
   return SMZ_OK;
 }
 
-int smz_read_roots(smz_engine* e, int32_t* visits, float* values, double* priors, float* rewards, void* stream) {
+int smz_read_roots(smz_engine* e, int32_t* visits, float* values, double* priors, float* rewards, int32_t* error_out,
+                   void* stream) {
   if (!e) return fail(SMZ_E_INVALID_ARG, "smz_read_roots: null engine");
   if (e->n_trees < 1) return fail(SMZ_E_STATE, "smz_read_roots: smz_root has not been called");
-  CU(cudaSetDevice(e->cfg.device));
-  smz_launch_read_roots(e->a, e->n_trees, visits, values, priors, rewards, (cudaStream_t)stream);
-  e->launches += 1;
+  ON_DEVICE(e);
+  smz_launch_read_roots(e->a, e->n_trees, visits, values, priors, rewards, error_out, (cudaStream_t)stream);
+  count_launches(e, 1);
   CU(cudaGetLastError());
   return SMZ_OK;
 }
@@ -519,9 +566,9 @@ int smz_select_actions(smz_engine* e, double temperature, const double* uniforms
   if (!e) return fail(SMZ_E_INVALID_ARG, "smz_select_actions: null engine");
   if (e->n_trees < 1) return fail(SMZ_E_STATE, "smz_select_actions: smz_root has not been called");
   if (!(temperature >= 0.0)) return fail(SMZ_E_INVALID_ARG, "smz_select_actions: temperature must be >= 0");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   smz_launch_select_actions(e->a, e->n_trees, temperature, uniforms, actions, policy, stored_policy, (cudaStream_t)stream);
-  e->launches += 1;
+  count_launches(e, 1);
   CU(cudaGetLastError());
   return SMZ_OK;
 }
@@ -529,7 +576,7 @@ int smz_select_actions(smz_engine* e, double temperature, const double* uniforms
 int smz_export_tree(smz_engine* e, int32_t tree, smz_tree_host* out, void* stream) {
   if (!e || !out) return fail(SMZ_E_INVALID_ARG, "smz_export_tree: null argument");
   if (tree < 0 || tree >= e->n_trees) return fail(SMZ_E_INVALID_ARG, "smz_export_tree: tree %d not in [0, %d)", tree, e->n_trees);
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   CU(cudaStreamSynchronize((cudaStream_t)stream));
   const SmzArena& a = e->a;
   const size_t M = a.M;
@@ -559,9 +606,10 @@ int smz_read_hidden(smz_engine* e, int32_t slot, float* out, void* stream) {
   if (!e || !out) return fail(SMZ_E_INVALID_ARG, "smz_read_hidden: null argument");
   if (!e->a.hidden) return fail(SMZ_E_STATE, "smz_read_hidden: engine has no internal network");
   if (slot < 0 || slot > e->a.N || e->n_trees < 1) return fail(SMZ_E_INVALID_ARG, "smz_read_hidden: bad slot");
-  CU(cudaSetDevice(e->cfg.device));
-  if (e->bf16) {
-    smz_bf16_read_hidden(e->a, slot, e->n_trees, out, (cudaStream_t)stream);
+  ON_DEVICE(e);
+  if (e->bf16 || e->tc32) {
+    if (e->bf16) smz_bf16_read_hidden(e->a, slot, e->n_trees, out, (cudaStream_t)stream);
+    else smz_tc32_read_hidden(e->a, slot, e->n_trees, out, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return SMZ_OK;
   }
@@ -576,7 +624,7 @@ int smz_read_record(smz_engine* e, float* policy, float* value, float* reward, i
   if (!e->a.rec_policy) return fail(SMZ_E_STATE, "smz_read_record: engine was created with record = 0");
   if (e->n_trees < 1) return fail(SMZ_E_STATE, "smz_read_record: smz_root has not been called");
   cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   const SmzArena& a = e->a;
   const size_t n = e->n_trees, N = a.N;
   if (policy) CU(cudaMemcpyAsync(policy, a.rec_policy, n * N * a.W * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -588,9 +636,9 @@ int smz_read_record(smz_engine* e, float* policy, float* value, float* reward, i
   return SMZ_OK;
 }
 
-int smz_stats(smz_engine* e, double* mean_leaf_depth, int64_t* launches, void* stream) {
+int smz_stats(smz_engine* e, double* mean_leaf_depth, int64_t* launches, int64_t* launches_total, void* stream) {
   if (!e) return fail(SMZ_E_INVALID_ARG, "smz_stats: null engine");
-  CU(cudaSetDevice(e->cfg.device));
+  ON_DEVICE(e);
   CU(cudaStreamSynchronize((cudaStream_t)stream));
   unsigned long long ds = 0;
   int err = 0;
@@ -601,6 +649,7 @@ int smz_stats(smz_engine* e, double* mean_leaf_depth, int64_t* launches, void* s
     *mean_leaf_depth = n > 0 ? (double)ds / n : 0.0;
   }
   if (launches) *launches = e->launches;
+  if (launches_total) *launches_total = e->launches_total;
   if (err == 1) return fail(SMZ_E_CAPACITY, "uniform tape exhausted during the search");
   if (err == 2) return fail(SMZ_E_STATE, "degenerate (NaN / all-zero) policy met during expansion");
   return SMZ_OK;

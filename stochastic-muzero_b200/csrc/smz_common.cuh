@@ -41,8 +41,9 @@ struct SmzArena {
   // the tail of the kernel that still gathers sim s in another CTA): index smz_row_index(a, sim, branch, row)
   int* rows;        // [2 parities][2 branches][B] tree ids
   int4* rows4;      // same order: {tree, parent hidden slot, action, 0} — one load per gathered row
-  uint4* xin;       // same order, bf16 network only (else null): the parent's hidden row (64 bf16 = 8 x 16 B), copied by the
-                    // descent so that the network step gathers with ONE dependent load instead of two
+  uint4* xin;       // same order, tensor-core networks only (else null): the parent's hidden row (xin_q x 16 B), copied by
+                    // the descent so that the network step gathers with ONE dependent load instead of two
+  int xin_q;        // 16-byte pieces per hidden row: 8 (64 bf16) or 16 (64 fp16 hi + 64 fp16 lo, SMZ_NET_TC32)
   int* error_flag;  // [1]
   unsigned long long* depth_sum;  // [1] sum of leaf depths (bench bookkeeping)
   long long* dbg;   // debug clock stamps (null unless SMZ_TREE_TIMELINE is set)

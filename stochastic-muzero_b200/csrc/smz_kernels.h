@@ -15,7 +15,7 @@ void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim
 // expand+backup of `sim` fused with the descent of `sim + 1` (internal-network loop)
 void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s);
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,
-                           cudaStream_t s);
+                           int* error_out, cudaStream_t s);
 void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s);
 void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperature, const double* u, int* actions,
                                double* policy, double* stored, cudaStream_t s);

@@ -53,7 +53,9 @@ __global__ void k_root_expand(SmzArena a, int n_trees, const float* __restrict__
     a.link[tb] = make_int2(1, -1);
     a.minmax[tree] = make_float2(__int_as_float(0x7f800000), __int_as_float(0xff800000));
     a.ucursor[tree] = cursor;
-    a.root_to_play[tree] = root_to_play ? root_to_play[tree] : 0;
+    // wrapped into [0, n_phases) like Player_cycle.global_step() (mcts.py:55-58): the backup indexes the sign table with it
+    const int rtp = root_to_play ? root_to_play[tree] % a.n_phases : 0;
+    a.root_to_play[tree] = rtp < 0 ? rtp + a.n_phases : rtp;
     a.path_len[tree] = 0;
     if (a.rec_root_policy)
       for (int i = 0; i < a.W; ++i) a.rec_root_policy[(size_t)tree * a.W + i] = i < n ? policy[(size_t)tree * pstride + i] : 0.f;
@@ -176,8 +178,9 @@ __global__ void k_backup_select_sm(SmzArena a, int n_trees, int sim, int n_tab) 
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_read_roots(SmzArena a, int n_trees, int* __restrict__ visits, float* __restrict__ values,
-                             double* __restrict__ priors, float* __restrict__ rewards) {
+                             double* __restrict__ priors, float* __restrict__ rewards, int* __restrict__ error_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && error_out) *error_out = *a.error_flag;
   if (i >= n_trees * a.A) return;
   const int tree = i / a.A, c = i % a.A;
   const size_t tb = (size_t)tree * a.M;
@@ -332,12 +335,11 @@ bool smz_tree_mirror_fits(const SmzArena& a, int lanes) {
 // The mirror kernel is the low-latency variant (one block of 128 threads per SM or two); with many blocks per SM the
 // arena-only kernel wins on occupancy (measured crossover on B200, cfg-2 shapes: ~16 k trees = 512 blocks).
 static bool mirror_pays(int blocks) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  static int sms_of[64] = {0};      // per device: engines of one process may live on different GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& sms = sms_of[dev & 63];
+  if (!sms && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
   return blocks <= 3 * sms;
 }
 
@@ -355,9 +357,9 @@ void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim
 }
 
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,
-                           cudaStream_t s) {
+                           int* error_out, cudaStream_t s) {
   const int n = n_trees * a.A;
-  k_read_roots<<<(n + 255) / 256, 256, 0, s>>>(a, n_trees, visits, values, priors, rewards);
+  k_read_roots<<<(n + 255) / 256, 256, 0, s>>>(a, n_trees, visits, values, priors, rewards, error_out);
 }
 
 void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperature, const double* u, int* actions,

@@ -245,14 +245,16 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
   const int branch = ((depth >> 1) & 1) ? SMZ_BRANCH_DYNAMICS : SMZ_BRANCH_AFTERSTATE;
   const int slot = (cbase == 1) ? 0 : (cbase - 1 - a.A) / a.Kmax + 1;
   // the parent's hidden row is requested now and stored once the row index is known (bf16 network: a.xin)
-  uint4 hcopy[(G < 8) ? 8 / G : 1];
+  uint4 hcopy[(G < 8) ? 8 / G : 1], hcopy2[(G < 8) ? 8 / G : 1];
   const bool copy_row = COMPACT && a.xin != nullptr && alive;
+  const bool wide_row = a.xin_q > 8;          // fp16 hi + lo rows (SMZ_NET_TC32): a second batch of 8 pieces
   if (copy_row) {
-    const uint4* src = reinterpret_cast<const uint4*>(a.hidden) + ((size_t)slot * a.B + tree) * 8;
+    const uint4* src = reinterpret_cast<const uint4*>(a.hidden) + ((size_t)slot * a.B + tree) * a.xin_q;
 #pragma unroll
     for (int j = 0; j < ((G < 8) ? 8 / G : 1); ++j) {
       const int idx = g.gl + j * G;
       hcopy[j] = idx < 8 ? src[idx] : make_uint4(0, 0, 0, 0);
+      if (wide_row) hcopy2[j] = idx < 8 ? src[8 + idx] : make_uint4(0, 0, 0, 0);
     }
   }
   int r = 0;
@@ -295,11 +297,12 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
   if (COMPACT) {
     const int rg = g.bcast(r, 0);
     if (copy_row) {
-      uint4* dst = a.xin + smz_row_index(a, sim, branch, rg) * 8;
+      uint4* dst = a.xin + smz_row_index(a, sim, branch, rg) * a.xin_q;
 #pragma unroll
       for (int j = 0; j < ((G < 8) ? 8 / G : 1); ++j) {
         const int idx = g.gl + j * G;
         if (idx < 8) dst[idx] = hcopy[j];
+        if (wide_row && idx < 8) dst[8 + idx] = hcopy2[j];
       }
     }
   }

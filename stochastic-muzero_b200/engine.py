@@ -16,7 +16,8 @@ from .weights import VISION_FLAT, ModelShape, VisionShape
 
 SEARCH_KEYS = ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha", "root_exploration_fraction",
                "num_simulations", "maxium_action_sample", "number_of_player", "custom_loop")
-_NET = {"external": _lib.NET_EXTERNAL, "fp32": _lib.NET_FP32, "bf16": _lib.NET_BF16, "vision": _lib.NET_VISION}
+_NET = {"external": _lib.NET_EXTERNAL, "fp32": _lib.NET_FP32, "bf16": _lib.NET_BF16, "vision": _lib.NET_VISION,
+        "tc32": _lib.NET_TC32}
 _RNG = {"philox": _lib.RNG_PHILOX, "tape": _lib.RNG_TAPE}
 
 
@@ -104,6 +105,7 @@ class SearchEngine:
         self._check(self.lib.smz_get_dims(self._h, C.byref(self.dims)))
         self.max_trees = int(max_trees)
         self.n_trees = 0
+        self.generation = 0       # bumped by every root(): views of an older search can tell that they are stale
         self._keep = {}           # tensors the engine holds raw pointers to
         # sqrt(n) * pb_c(n) with numpy's sqrt/log, exactly as monte_carlo_tree_search.py:236-237 evaluates
         # `np.sqrt(parent.visit_count) * pb_c` on this host (the product is then multiplied by the prior)
@@ -187,6 +189,7 @@ class SearchEngine:
         self._check(self.lib.smz_root(self._h, n, self._ptr(obs_t), self._ptr(pol_t), self._ptr(rtp), int(bool(train)),
                                       self._ptr(dr), self._stream))
         self.n_trees = n
+        self.generation += 1
 
     def _pad_policy(self, p, name):
         W = self.dims.policy_stride
@@ -208,6 +211,10 @@ class SearchEngine:
 
     def net_step(self, sim):
         self._check(self.lib.smz_net_step(self._h, int(sim), self._stream))
+
+    def backup_select(self, sim):
+        """The fused tree step of the captured loop (expansion + backup of `sim`, descent of `sim + 1`)."""
+        self._check(self.lib.smz_backup_select(self._h, int(sim), self._stream))
 
     def expand_backup(self, sim, policy=None, value=None, reward=None):
         if policy is None:
@@ -254,10 +261,21 @@ class SearchEngine:
         n, A = self.n_trees, self.A
         if out is None:
             out = {"visits": self._new(n, A, dtype=torch.int32), "root_values": self._new(n, dtype=torch.float32),
-                   "priors": self._new(n, A, dtype=torch.float64), "rewards": self._new(n, A, dtype=torch.float32)}
+                   "priors": self._new(n, A, dtype=torch.float64), "rewards": self._new(n, A, dtype=torch.float32),
+                   "error": self._new(1, dtype=torch.int32)}
         self._check(self.lib.smz_read_roots(self._h, self._ptr(out.get("visits")), self._ptr(out.get("root_values")),
-                                            self._ptr(out.get("priors")), self._ptr(out.get("rewards")), self._stream))
+                                            self._ptr(out.get("priors")), self._ptr(out.get("rewards")),
+                                            self._ptr(out.get("error")), self._stream))
         return out
+
+    @staticmethod
+    def raise_for_error(code: int):
+        """Error flag of a search (smz_read_roots) -> the exception the reference would have raised."""
+        if code == 1:
+            raise SmzError("uniform tape exhausted during the search")
+        if code == 2:       # np.random.choice at monte_carlo_tree_search.py:208 / :294 raises ValueError here
+            raise ValueError("probabilities contain NaN or sum to zero: a policy met during expansion was degenerate "
+                             "(np.random.choice raises at this point in the reference)")
 
     def select_actions(self, temperature: float, uniforms=None):
         """game.py:179-235 for every tree: -> dict(actions int32[n], policy f64[n,A], stored_policy f64[n,A])."""
@@ -285,9 +303,9 @@ class SearchEngine:
         return rec
 
     def stats(self):
-        depth, launches = C.c_double(), C.c_int64()
-        self._check(self.lib.smz_stats(self._h, C.byref(depth), C.byref(launches), self._stream))
-        return {"mean_leaf_depth": depth.value, "launches": launches.value}
+        depth, launches, total = C.c_double(), C.c_int64(), C.c_int64()
+        self._check(self.lib.smz_stats(self._h, C.byref(depth), C.byref(launches), C.byref(total), self._stream))
+        return {"mean_leaf_depth": depth.value, "launches": launches.value, "launches_total": total.value}
 
     def export_arena(self, tree: int) -> Dict[str, np.ndarray]:
         """One tree in arena order (see smz_tree_host)."""

@@ -16,6 +16,7 @@ Two ways a model can be attached:
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -141,26 +142,51 @@ def _node_tree(dump, hidden_fetch=None):
     return nodes[0]
 
 
+class StaleSearchError(RuntimeError):
+    """A view of a finished search was used after the engine's arena had been reused by a newer search."""
+
+
 class BatchedRoots:
-    """Result of ``run_batch``: root statistics of B trees as device tensors + lazy ``Node`` views."""
+    """Result of ``run_batch``: root statistics of B trees as device tensors + lazy ``Node`` views.
+
+    Lifetime: ``visit_counts`` / ``priors`` / ``rewards`` / ``root_values`` are tensors of their own and stay valid.
+    ``roots[i]``, ``select_actions()`` and the lazy ``Node.hidden_state`` of a returned tree read the engine's arena,
+    which the NEXT ``run`` / ``run_batch`` on the same ``Monte_carlo_tree_search`` reuses: from then on they raise
+    ``StaleSearchError`` instead of silently describing the newer search (the reference's roots are
+    self-contained; take what you need before searching again, or use a second Monte_carlo_tree_search)."""
 
     def __init__(self, engine: SearchEngine, stats):
         self._engine = engine
+        self._generation = engine.generation
         self.visit_counts = stats["visits"]       # int32 [B, A]
         self.priors = stats["priors"]             # float64 [B, A]
         self.rewards = stats["rewards"]           # float32 [B, A]
         self.root_values = stats["root_values"]   # float32 [B]
+        self.error = stats.get("error")           # int32 [1] device: the search's error flag (engine.raise_for_error)
 
     def __len__(self):
         return int(self.visit_counts.shape[0])
 
+    def _live(self):
+        if self._engine.generation != self._generation or not self._engine._h.value:
+            raise StaleSearchError("this search's arena has been reused by a later run()/run_batch() (or the engine "
+                                   "was reset); read roots[i] / select_actions() / hidden_state before searching again")
+        return self._engine
+
+    def raise_if_failed(self):
+        """Synchronises on the read-out and raises what the reference would have raised inside ``run``
+        (np.random.choice's ValueError on a NaN / all-zero policy, monte_carlo_tree_search.py:208/:294)."""
+        if self.error is not None:
+            self._engine.raise_for_error(int(self.error.item()))
+        return self
+
     def select_actions(self, temperature: float = 0.0, uniforms=None):
         """Batched Game.policy_step / store_search_statistics (game.py:179-235) on the device:
         dict(actions, policy, stored_policy); root values are `self.root_values`."""
-        return self._engine.select_actions(temperature, uniforms)
+        return self._live().select_actions(temperature, uniforms)
 
     def __getitem__(self, i) -> Node:
-        return _node_tree(self._engine.export_tree(int(i)), self._hidden_fetcher(int(i)))
+        return _node_tree(self._live().export_tree(int(i)), self._hidden_fetcher(int(i)))
 
     @property
     def roots(self):
@@ -173,6 +199,7 @@ class BatchedRoots:
         A, kmax = eng.A, eng.dims.max_children
 
         def fetch(node_index, _ar={}):
+            self._live()
             if "cb" not in _ar:
                 _ar["cb"] = eng.export_arena(tree)["child_base"]
             cb = int(_ar["cb"][node_index])
@@ -192,14 +219,19 @@ class Monte_carlo_tree_search():
                  maxium_action_sample=2,
                  number_of_player=1,
                  custom_loop=None,
-                 *, net="fp32", device=None, seed=None, max_batch=None):
+                 *, net="fp32", device=None, seed=None, max_batch=None, tree_id_offset=None):
         """Same nine arguments as the reference (:76-85).  Keyword-only extras: ``net`` ("fp32" exact
         mode or "bf16" tensor-core mode for the fused MLP step), ``device`` (CUDA ordinal), ``seed``
         (Philox key; default drawn from numpy's global RNG so ``np.random.seed`` reproduces runs),
-        ``max_batch`` (arena capacity reserved for ``run_batch``)."""
+        ``max_batch`` (arena capacity reserved for ``run_batch``), ``tree_id_offset`` (global id of local tree 0:
+        the Philox streams are keyed by (seed, global tree id), so ranks of a sharded self-play that seed
+        numpy identically still draw different noise; default rank * max_batch when torch.distributed is
+        initialised, else 0)."""
         self._net, self._device, self._seed, self._max_batch = net, device, seed, max_batch
+        self._tree_id_offset = tree_id_offset
         self._engines = {}
         self._weights_seen = {}
+        self._per_model, self._pinned = weakref.WeakKeyDictionary(), {}
         self._run_counter = 0
         self.reset(pb_c_base, pb_c_init, discount, root_dirichlet_alpha, root_exploration_fraction,
                    num_simulations, maxium_action_sample, number_of_player, custom_loop)
@@ -277,34 +309,65 @@ class Monte_carlo_tree_search():
             hasattr(model, f"{n}_function") for n in ("representation", "prediction", "afterstate_prediction",
                                                       "afterstate_dynamics", "dynamics", "encoder"))
 
+    def _model_cache(self, model) -> dict:
+        """Per-model scratch (packed vision blob, torch back-end), dropped with the model: keyed by a weak reference,
+        not by id() — an id can be reused by another object after garbage collection."""
+        try:
+            return self._per_model.setdefault(model, {})
+        except TypeError:                    # not weak-referenceable / unhashable: pin it, so its id stays its own
+            return self._pinned.setdefault(id(model), (model, {}))[1]
+
     def _next_seed(self):
         self._run_counter += 1
         return (self._base_seed() + 0x9E3779B97F4A7C15 * self._run_counter) & 0xFFFFFFFFFFFFFFFF
 
+    def _offset(self, batch):
+        """Global id of local tree 0 (see ``tree_id_offset`` in __init__)."""
+        if self._tree_id_offset is not None:
+            return int(self._tree_id_offset)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank() * max(int(batch), self._max_batch or 1)
+        return 0
+
+    # engines hold ctypes handles and device memory: copies / pickles (the reference ships the search object to ray
+    # workers, self_play.py:240-256) carry the configuration only and rebuild their engines lazily
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_engines"], state["_weights_seen"] = {}, {}
+        state["_pinned"] = {}
+        del state["_per_model"]
+        state["root"] = state["node"] = state["model"] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._per_model = weakref.WeakKeyDictionary()
+
     # ------------------------------------------------------------------------------------------
-    def run_batch(self, observations, model=None, train=True, root_to_play=None) -> BatchedRoots:
+    def run_batch(self, observations, model=None, train=True, root_to_play=None, check=True) -> BatchedRoots:
         """B independent searches in one call.  ``observations``: float tensor/array [B, obs_dim]
-        (host or device).  Returns BatchedRoots (device tensors; ``roots[i]`` gives a Node view)."""
+        (host or device).  Returns BatchedRoots (device tensors; ``roots[i]`` gives a Node view).
+        ``check`` (default): wait for the search and raise if it met a degenerate policy, like the reference's
+        np.random.choice does; ``check=False`` returns without synchronising (``roots.raise_if_failed()`` later)."""
         if not self._is_fusable(model):
-            return self._run_batch_external(observations, model, train, root_to_play)
+            roots = self._run_batch_external(observations, model, train, root_to_play)
+            return roots.raise_if_failed() if check else roots
         self.model = model
         vision = getattr(model, "model_structure", None) == "vision_model"
         obs = observations if torch.is_tensor(observations) else torch.as_tensor(np.asarray(observations))
         obs = obs.reshape(obs.shape[0], -1)
         if vision:
             # vision (ResNet-v2) family: fp32 CUDA-core network step, observations [B, 3, 98, 98]
-            if isinstance(model, PackedModel):
-                shape = model.shape
-            else:
-                shape = self._weights_seen.get(("vshape", id(model)))
+            cache = self._model_cache(model)
             ver = weights_version(model)
-            if shape is None or self._weights_seen.get(("vver", id(model))) != ver:
+            if cache.get("vver") != ver:
                 blob, shape = pack_vision_weights(model) if not isinstance(model, PackedModel) else (model.blob, model.shape)
-                self._weights_seen[("vshape", id(model))], self._weights_seen[("vblob", id(model))] = shape, blob
-                self._weights_seen[("vver", id(model))] = ver
+                cache["vshape"], cache["vblob"], cache["vver"] = shape, blob, ver
+            shape = cache["vshape"]
             eng, key = self._engine("vision", obs.shape[0], shape.action_dim, shape.action_dim, shape)
             if self._weights_seen.get(key) != ver:
-                eng.set_weights(self._weights_seen[("vblob", id(model))])
+                eng.set_weights(cache["vblob"])
                 self._weights_seen[key] = ver
         else:
             shape = shape_of(model)
@@ -314,10 +377,11 @@ class Monte_carlo_tree_search():
                 blob, _ = pack_weights(model)
                 eng.set_weights(blob)
                 self._weights_seen[key] = ver
-        eng.set_seed(self._next_seed())
+        eng.set_seed(self._next_seed(), self._offset(obs.shape[0]))
         eng.root(obs=obs, root_to_play=root_to_play, train=train)
         eng.simulate(self.num_simulations)
-        return BatchedRoots(eng, eng.read_roots())
+        roots = BatchedRoots(eng, eng.read_roots())
+        return roots.raise_if_failed() if check else roots
 
     def _run_batch_external(self, observations, model, train, root_to_play):
         """Any other model family: tree kernels in the engine, network step = five batched device
@@ -328,11 +392,13 @@ class Monte_carlo_tree_search():
             backend = model
         elif all(hasattr(model, f"{n}_function") for n in ("representation", "prediction", "afterstate_prediction",
                                                            "afterstate_dynamics", "dynamics")):
-            key = ("backend", id(model))
-            backend = self._weights_seen.get(key)
-            if backend is None:
-                backend = self._weights_seen[key] = batched_model.ReferenceModuleBackend(
+            cache = self._model_cache(model)
+            ver = weights_version(model)
+            if cache.get("backend_ver") != ver:      # the back-end works on its own device copy of the modules
+                cache["backend"] = batched_model.ReferenceModuleBackend(
                     model, device=f"cuda:{self._device if self._device is not None else torch.cuda.current_device()}")
+                cache["backend_ver"] = ver
+            backend = cache["backend"]
         else:
             raise TypeError("run_batch needs a reference-style Muzero or an object with the five batched "
                             "network functions (see batched_model.py)")
@@ -340,7 +406,7 @@ class Monte_carlo_tree_search():
         A = int(getattr(backend, "A", 0)) or int(getattr(model, "action_dimension"))
         C = int(getattr(backend, "C", A))
         eng, _ = self._engine("external", obs.shape[0], A, C)
-        eng.set_seed(self._next_seed())
+        eng.set_seed(self._next_seed(), self._offset(obs.shape[0]))
         store = batched_model.run_search(eng, backend, obs, self.num_simulations, root_to_play, train)
         roots = BatchedRoots(eng, eng.read_roots())
         roots.hidden_store = store
@@ -372,7 +438,7 @@ class Monte_carlo_tree_search():
         policy = np.asarray(policy, dtype=np.float32).reshape(1, -1)
         A = policy.shape[1]
         eng, _ = self._engine("external", 1, A, getattr(model, "chance_dimension", A))
-        eng.set_seed(self._next_seed())
+        eng.set_seed(self._next_seed(), self._offset(1))
         eng.root(root_policy=policy, root_to_play=torch.tensor([to_play], dtype=torch.int32), train=train)
         hidden = {0: h0}
         for sim in range(self.num_simulations):
@@ -387,6 +453,7 @@ class Monte_carlo_tree_search():
             hidden[sim + 1] = h
             eng.expand_backup(sim, np.asarray(policy, dtype=np.float32).reshape(1, -1),
                               np.array([value], dtype=np.float32), np.array([reward], dtype=np.float32))
+        eng.raise_for_error(int(eng.read_roots()["error"].item()))
         dump = eng.export_tree(0)
         kmax = eng.dims.max_children
         arena_cb = eng.export_arena(0)["child_base"]

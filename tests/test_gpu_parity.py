@@ -103,10 +103,23 @@ def _net_engine(z, B=64, **kw):
     return eng
 
 
+# the two reference-precision network steps: fp32 on the CUDA cores, and the tcgen05 chain on fp16 hi/lo split operands
+# (three products per K-step, fp32 accumulate; SMZ_TC32_POLY=1 adds the polynomial expm1 for small |x|)
+REF_PRECISION_NETS = ["fp32", "tc32", "tc32-poly"]
+
+
+def _ref_precision_engine(z, net, monkeypatch, **kw):
+    monkeypatch.delenv("SMZ_TC32_POLY", raising=False)
+    if net == "tc32-poly":
+        monkeypatch.setenv("SMZ_TC32_POLY", "1")
+    return _net_engine(z, net=net.split("-")[0], **kw)
+
+
+@pytest.mark.parametrize("net", REF_PRECISION_NETS)
 @pytest.mark.parametrize("name", golden_io.net_cases())
-def test_fp32_network_step_matches_reference_inference(name):
+def test_fp32_network_step_matches_reference_inference(name, net, monkeypatch):
     z = golden_io.load_net_case(name)
-    eng = _net_engine(z)
+    eng = _ref_precision_engine(z, net, monkeypatch)
     tol = dict(atol=NET_ATOL, rtol=1e-5)
     np.testing.assert_allclose(eng.net_eval("repr", z["obs"])["hidden"].cpu().numpy(), z["repr_h"], **tol)
     o = eng.net_eval("pred", z["repr_h"])
@@ -201,8 +214,9 @@ def _oracle_cfg(c):
                                                 "maxium_action_sample", "number_of_player", "custom_loop")})
 
 
+@pytest.mark.parametrize("net", REF_PRECISION_NETS)
 @pytest.mark.parametrize("name", ["mlp450_seed0", "ckpt450", "mlp_small", "mlp_l0"])
-def test_full_search_with_internal_network_vs_reference(name):
+def test_full_search_with_internal_network_vs_reference(name, net, monkeypatch):
     """Real-MLP recorded searches: obs + recorded draws in, engine runs its own fp32 network.
     (1) every network output the engine produced matches what the reference produced at the same
     simulation within 1e-5 as long as the paths coincide, (2) replaying the engine's OWN recorded
@@ -212,7 +226,7 @@ def test_full_search_with_internal_network_vs_reference(name):
     zn = golden_io.load_net_case(name)
     c = z["config"]
     B, N = len(z["n_nodes"]), c["num_simulations"]
-    eng = _net_engine(zn, B=B, N=N, K=c["maxium_action_sample"], rng="tape", record=True)
+    eng = _ref_precision_engine(zn, net, monkeypatch, B=B, N=N, K=c["maxium_action_sample"], rng="tape", record=True)
     eng.set_uniform_tape(torch.from_numpy(z["uniforms"]))
     eng.root(obs=torch.from_numpy(z["obs"]), train=True, dirichlet=torch.from_numpy(z["dirichlet"]))
     eng.simulate(N)
@@ -354,7 +368,9 @@ def test_shard_invariance_philox_keyed_by_global_tree_id():
         parts.append({k: v.cpu().numpy() for k, v in e.read_roots().items()})
         e.close()
     for k in full:
-        assert np.array_equal(full[k], np.concatenate([p[k] for p in parts])), k
+        if k != "error":            # one flag per engine, not per tree
+            assert np.array_equal(full[k], np.concatenate([p[k] for p in parts])), k
+    assert full["error"][0] == 0 and all(p["error"][0] == 0 for p in parts)
     whole.close()
 
 
@@ -370,7 +386,7 @@ def test_wide_chance_codebook_full_search_config3_shape():
     B, seed = 64, 31
     g = np.random.default_rng(0)
     obs = (g.integers(0, 12, (B, 16)) / 16.0).astype(np.float32)
-    for net in ("fp32", "bf16"):
+    for net in ("fp32", "bf16", "tc32"):
         eng = SearchEngine(search, 4, 32, max_trees=B, model_shape=shape, net=net, rng="philox", seed=seed, record=True)
         eng.set_weights(random_blob(shape, seed=3))
         eng.root(obs=obs, train=True); eng.simulate(100)
@@ -695,14 +711,14 @@ def test_partial_batch_equals_exact_size_engine():
     obs = torch.randn(77, 4, generator=torch.Generator().manual_seed(9))
     out = []
     for cap in (77, 300):
-        for net in ("fp32", "bf16"):
+        for net in ("fp32", "bf16", "tc32"):
             e = _net_engine(zn, B=cap, N=20, net=net, rng="philox", seed=66)
             e.root(obs=obs, train=True); e.simulate(20)
             r = e.read_roots()
             assert r["visits"].shape == (77, 2)
             out.append((net, r["visits"].cpu().numpy(), r["root_values"].cpu().numpy()))
             e.close()
-    for net in ("fp32", "bf16"):
+    for net in ("fp32", "bf16", "tc32"):
         a, b = [o for o in out if o[0] == net]
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), f"{net}: capacity changed the result"
 
@@ -781,3 +797,150 @@ def test_kernel_variants_give_the_same_search(monkeypatch, variant):
     np.testing.assert_allclose(rec["sim_policy"], ref_rec["sim_policy"], atol=1e-6)
     np.testing.assert_allclose(rec["sim_value"], ref_rec["sim_value"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(roots["root_values"], ref_roots["root_values"], rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round-2 boundary behaviour: error flag surfaced, root_to_play wrapped, stale views refused
+# ---------------------------------------------------------------------------------------------------
+def test_degenerate_policy_raises_like_numpy_choice():
+    """A NaN policy makes np.random.choice raise inside the reference's expansion (mcts.py:294); the engine
+    sets its error flag, delivers it with the root read-out and the drop-in raises ValueError."""
+    from stochastic_muzero_b200 import Monte_carlo_tree_search, SearchEngine
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=4, maxium_action_sample=2,
+                  number_of_player=1, custom_loop=None)
+    eng = SearchEngine(search, 2, 2, max_trees=3, net="external", rng="philox", seed=1)
+    eng.root(root_policy=torch.full((3, 2), 0.5), train=False)
+    bad = torch.tensor([[0.5, 0.5], [float("nan"), float("nan")], [0.5, 0.5]])
+    eng.select(0)
+    eng.expand_backup(0, bad, torch.zeros(3), torch.zeros(3))
+    assert int(eng.read_roots()["error"].item()) == 2
+    with pytest.raises(ValueError, match="degenerate"):
+        eng.raise_for_error(2)
+    eng.close()
+
+    class NaNBackend:          # batched back-end whose afterstate policy head returns NaN
+        A = C = 2
+
+        def representation(self, obs):
+            return torch.zeros(obs.shape[0], 3, device="cuda")
+
+        def prediction(self, h):
+            return torch.full((h.shape[0], 2), 0.5, device="cuda"), torch.zeros(h.shape[0], device="cuda")
+
+        def afterstate_dynamics(self, h, a):
+            return h
+
+        def afterstate_prediction(self, h):
+            return torch.full((h.shape[0], 2), float("nan"), device="cuda"), torch.zeros(h.shape[0], device="cuda")
+
+        def dynamics(self, h, c):
+            return torch.zeros(h.shape[0], device="cuda"), h
+    mcts = Monte_carlo_tree_search(num_simulations=4, discount=0.997, seed=3)
+    with pytest.raises(ValueError, match="degenerate"):
+        mcts.run_batch(torch.zeros(5, 4), NaNBackend(), train=False)
+    roots = mcts.run_batch(torch.zeros(5, 4), NaNBackend(), train=False, check=False)      # asynchronous form
+    with pytest.raises(ValueError):
+        roots.raise_if_failed()
+
+
+def test_root_to_play_is_wrapped_into_the_player_cycle():
+    """Values outside [0, n_phases) used to index the sign table out of bounds; they are wrapped like
+    Player_cycle.global_step() wraps its counter, and the exported tree agrees with what the device did."""
+    z = golden_io.load_tree_case("a3c5k3_n30_p2")
+    c = z["config"]
+    B, N = len(z["n_nodes"]), c["num_simulations"]
+    n_ph = 2
+
+    def run(rtp):
+        eng = _engine_for(z, max_trees=B, net="external", rng="tape")
+        eng.set_uniform_tape(torch.from_numpy(z["uniforms"]))
+        eng.root(root_policy=torch.from_numpy(z["root_policy"]), root_to_play=torch.from_numpy(rtp), train=z["train"],
+                 dirichlet=torch.from_numpy(z["dirichlet"]))
+        pol, val, rew = (torch.from_numpy(z[k]).cuda() for k in ("sim_policy", "sim_value", "sim_reward"))
+        for s in range(N):
+            eng.select(s)
+            eng.expand_backup(s, pol[:, s].contiguous(), val[:, s].contiguous(), rew[:, s].contiguous())
+        out = [eng.export_tree(b) for b in range(B)]
+        eng.close()
+        return out
+    base = z["exp_root_to_play"].astype(np.int32)
+    ref = run(base)
+    for shift in (n_ph * 7, -n_ph * 3):
+        got = run(base + shift)
+        for b in range(B):
+            golden_io.assert_dump_equal(got[b], ref[b], f"root_to_play + {shift} [{b}]")
+            golden_io.assert_dump_equal(got[b], golden_io.expected_dump(z, b), f"wrapped vs reference [{b}]")
+
+
+def test_views_of_an_older_search_are_refused():
+    from fake_muzero import FakeMuzero
+    from stochastic_muzero_b200 import Monte_carlo_tree_search, StaleSearchError
+    zn = golden_io.load_net_case("mlp450_seed0")
+    model = FakeMuzero(zn["weights"], *[int(v) for v in zn["dims"]])
+    mcts = Monte_carlo_tree_search(discount=0.997, num_simulations=10, seed=3)
+    first = mcts.run_batch(torch.randn(8, 4), model, train=True)
+    kept = first.visit_counts.clone()
+    node = first[2]
+    assert node.hidden_state.shape == (1, 61)             # fetched while the search is current
+    root1 = mcts.run(observation=torch.randn(1, 4), model=model, train=True)
+    assert torch.equal(first.visit_counts, kept)          # plain result tensors stay valid ...
+    with pytest.raises(StaleSearchError):                 # ... arena-backed views do not
+        first[0]
+    with pytest.raises(StaleSearchError):
+        first.select_actions(1.0)
+    mcts.run(observation=torch.randn(1, 4), model=model, train=True)
+    with pytest.raises(StaleSearchError):
+        root1.hidden_state
+    assert sum(c.visit_count for c in root1.children.values()) == 10      # materialised statistics survive
+
+
+def test_launch_counters_and_real_tree_step_hook():
+    """smz_stats counts the kernels of the last search and since creation; smz_backup_select runs the fused
+    tree step of the captured loop stand-alone and gives the same search as smz_simulate."""
+    zn = golden_io.load_net_case("mlp450_seed0")
+    B, N = 200, 12
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(5))
+    for net in ("fp32", "bf16", "tc32"):
+        a = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=8)
+        a.root(obs=obs, train=True); a.simulate(N)
+        st = a.stats()
+        assert st["launches"] == 3 + 1 + 2 * N and st["launches_total"] >= st["launches"]
+        ref = a.read_roots()
+        b = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=8)
+        b.root(obs=obs, train=True)
+        b.select(0)
+        for s in range(N):
+            b.net_step(s)
+            if s + 1 < N:
+                b.backup_select(s)
+            else:
+                b.expand_backup(s)
+        got = b.read_roots()
+        assert torch.equal(got["visits"], ref["visits"]) and torch.equal(got["root_values"], ref["root_values"])
+        with pytest.raises(ValueError, match="no successor"):
+            b.backup_select(N - 1)
+        a.close(); b.close()
+
+
+def test_tc32_search_agrees_with_the_fp32_cuda_core_search():
+    """Both reference-precision network steps drive the same search: same seeds, 512 trees x 50 simulations on
+    the trained checkpoint — identical visit vectors for (nearly) all trees (a sub-1e-6 score tie may flip), root
+    values within the scalar tolerance, hidden states within 1e-5, and the ragged last tile handled."""
+    zn = golden_io.load_net_case("ckpt450")
+    B, N = 500, 50
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(21)) * 0.1
+    out = {}
+    for net in ("fp32", "tc32"):
+        e = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=77)
+        e.root(obs=obs, train=True); e.simulate(N)
+        r = e.read_roots()
+        assert int(r["error"].item()) == 0
+        out[net] = (r["visits"].cpu().numpy(), r["root_values"].cpu().numpy(), e.read_hidden(0).cpu().numpy(),
+                    e.read_hidden(1).cpu().numpy())
+        e.close()
+    same = (out["fp32"][0] == out["tc32"][0]).all(1)
+    assert same.mean() >= 0.99, f"only {same.mean():.4f} of the trees have identical visit vectors"
+    np.testing.assert_allclose(out["tc32"][1][same], out["fp32"][1][same], **SCALAR_TOL)
+    np.testing.assert_allclose(out["tc32"][2], out["fp32"][2], atol=NET_ATOL, rtol=1e-5)
+    np.testing.assert_allclose(out["tc32"][3], out["fp32"][3], atol=NET_ATOL, rtol=1e-5)

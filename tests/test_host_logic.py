@@ -219,3 +219,20 @@ def test_markstein_division_is_exact_for_tabulated_divisors():
         rem = rn32(Fraction(float(x)) - Fraction(float(q)) * Fraction(float(d)))
         got = rn32(Fraction(float(q)) + Fraction(float(rem)) * Fraction(float(r)))
         assert got == np.float32(x / d), (x, d)
+
+
+def test_search_object_can_be_copied_and_pickled():
+    """The reference hands the search object to ray workers (self_play.py:240-256): copies carry the nine
+    parameters and the seed bookkeeping, never engine handles."""
+    import copy
+    import pickle
+    from stochastic_muzero_b200 import Monte_carlo_tree_search
+    m = Monte_carlo_tree_search(discount=0.997, num_simulations=7, maxium_action_sample=3, seed=11, tree_id_offset=64)
+    m._engines["sentinel"] = object()          # stands for a live engine (ctypes handle: not picklable)
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone._engines == {} and clone._weights_seen == {}
+        assert (clone.discount, clone.num_simulations, clone.maxium_action_sample) == (0.997, 7, 3)
+        assert clone._offset(16) == 64 and clone._base_seed() == 11
+        assert clone.cycle.global_step() == 0
+    m._engines.clear()
+    assert Monte_carlo_tree_search(num_simulations=3, max_batch=32)._offset(8) == 0     # no process group: rank 0
