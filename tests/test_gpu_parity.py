@@ -944,3 +944,114 @@ def test_tc32_search_agrees_with_the_fp32_cuda_core_search():
     np.testing.assert_allclose(out["tc32"][1][same], out["fp32"][1][same], **SCALAR_TOL)
     np.testing.assert_allclose(out["tc32"][2], out["fp32"][2], atol=NET_ATOL, rtol=1e-5)
     np.testing.assert_allclose(out["tc32"][3], out["fp32"][3], atol=NET_ATOL, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size runs of the other BASELINE configs: size-independent properties on every tree + sampled oracle replay
+# ---------------------------------------------------------------------------------------------------
+def _full_size_case(search, shape, A, C, B, net, seed, obs, sample, what):
+    from stochastic_muzero_b200 import SearchEngine
+    from stochastic_muzero_b200.weights import random_blob
+    N = search["num_simulations"]
+    eng = SearchEngine(search, A, C, max_trees=B, model_shape=shape, net=net, rng="philox", seed=seed, record=True)
+    eng.set_weights(random_blob(shape, seed=0))
+    eng.root(obs=obs, train=True)
+    eng.simulate(N)
+    st = eng.stats()                                             # raises on a device error flag
+    roots = {k: v.cpu().numpy() for k, v in eng.read_roots().items()}
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    assert roots["error"][0] == 0
+    assert (roots["visits"].sum(1) == N).all() and (roots["visits"] >= 0).all()       # one root child per simulation
+    assert np.allclose(roots["priors"].sum(1), 1.0, atol=1e-6) and (roots["priors"] > 0).all()
+    assert np.isfinite(roots["root_values"]).all()
+    bound = np.abs(rec["sim_reward"]).max() / (1 - search["discount"]) + np.abs(rec["sim_value"]).max()
+    assert (np.abs(roots["root_values"]) <= bound).all()
+    width = np.where(rec["sim_branch"] == 1, A, C)
+    psum = rec["sim_policy"].sum(2)
+    assert np.allclose(psum, 1.0, atol=2e-5), "a recorded policy row does not sum to 1"
+    cols = np.arange(rec["sim_policy"].shape[2])[None, None, :]
+    assert (rec["sim_policy"][cols >= width[:, :, None]] == 0).all(), "policy mass beyond the head's width"
+    assert set(np.unique(rec["sim_branch"])) <= {0, 1} and (rec["sim_branch"][:, 0] == 0).all()
+    assert (rec["sim_reward"][rec["sim_branch"] == 0] == 0).all()                    # afterstate pair has no reward
+    assert 1.5 < st["mean_leaf_depth"] < 12.0
+    # idempotence: same seed, same observations => the same statistics (atomics only order the compacted rows)
+    eng.set_seed(seed); eng.root(obs=obs, train=True); eng.simulate(N)
+    again = eng.read_roots()
+    assert np.array_equal(again["visits"].cpu().numpy(), roots["visits"])
+    assert np.array_equal(again["root_values"].cpu().numpy(), roots["root_values"])
+    cfg = O.SearchConfig(**search)
+    for b in sample:
+        b = int(b)
+        model = O.TapeModel(rec["root_policy"][b, :A], rec["sim_policy"][b], width[b], rec["sim_value"][b], rec["sim_reward"][b])
+        tree = O.search(cfg, model, O.PhiloxUniforms(seed, b), train=True, dirichlet=rec["dirichlet"][b])
+        got = eng.export_tree(b)
+        golden_io.assert_dump_equal(got, tree.dump(), f"{what}[{net}][{b}]")
+    eng.close()
+
+
+@pytest.mark.parametrize("net", ["bf16", "tc32"])
+def test_full_size_config3_8192_trees_100_simulations_wide_codebook(net):
+    """BASELINE configs[2] at full size: 8192 trees x 100 simulations, 4 actions, 32 chance codes, K = 32 (random
+    subsets never trigger: every head's children are all kept), synthetic 4x4 boards."""
+    from stochastic_muzero_b200 import ModelShape
+    shape = ModelShape(obs_dim=16, action_dim=4, chance_dim=32, state_dim=61, hidden_dim=126, num_hidden_layers=4)
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=100, maxium_action_sample=32,
+                  number_of_player=1, custom_loop=None)
+    B = 8192
+    obs = (torch.randint(0, 12, (B, 16), generator=torch.Generator().manual_seed(0)).float() / 16.0)
+    sample = [0, 63, 64, 4095, 4096, 8191] + list(np.random.default_rng(1).choice(B, 6, replace=False))
+    _full_size_case(search, shape, 4, 32, B, net, 303, obs, sample, "cfg3")
+
+
+def test_full_size_config4_65536_trees_50_simulations():
+    """BASELINE configs[3] on one GPU: 65536 trees x 50 simulations (the large-batch kernels: 128-row chain tiles,
+    arena-only tree step), bf16 network step."""
+    from stochastic_muzero_b200 import ModelShape
+    shape = ModelShape(4, 2, 2, 61, 126, 4)
+    search = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.997, root_dirichlet_alpha=0.25,
+                  root_exploration_fraction=0.25, num_simulations=50, maxium_action_sample=2,
+                  number_of_player=1, custom_loop=None)
+    B = 65536
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(0))
+    sample = [0, 127, 128, 32767, 32768, 65535] + list(np.random.default_rng(2).choice(B, 10, replace=False))
+    _full_size_case(search, shape, 2, 2, B, "bf16", 404, obs, sample, "cfg4")
+
+
+# ---------------------------------------------------------------------------------------------------
+# what the bf16 throughput mode does to the SEARCH RESULT (DESIGN.md §2: stated thresholds)
+# ---------------------------------------------------------------------------------------------------
+# fraction of trees with an identical root visit vector / the same most-visited action, and the 99th percentile of the
+# relative root-value deviation, bf16 vs fp32-grade (tc32) search on the same seeds, 4096 trees x 50 simulations.
+# Measured on B200 (tools/diag_bf16_agreement.py): random init 0.9998 / 1.0000 / 0; checkpoint 450 0.908 / 0.993 / 1.5e-2.
+BF16_SEARCH_AGREEMENT = {"mlp450_seed0": dict(identical=0.99, same_action=0.999, value_p99=1e-3),
+                         "ckpt450": dict(identical=0.85, same_action=0.98, value_p99=3e-2)}
+
+
+@pytest.mark.parametrize("name", sorted(BF16_SEARCH_AGREEMENT))
+def test_bf16_search_result_fidelity_against_reference_precision(name):
+    zn = golden_io.load_net_case(name)
+    B, N = 4096, 50
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(0)) * 0.1
+    res = {}
+    for net in ("fp32", "tc32", "bf16"):
+        eng = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=11)
+        eng.root(obs=obs, train=True); eng.simulate(N)
+        r = eng.read_roots()
+        assert int(r["error"].item()) == 0
+        res[net] = (r["visits"].cpu().numpy(), r["root_values"].cpu().numpy())
+        eng.close()
+
+    def agreement(a, b):
+        va, vb = res[a][0], res[b][0]
+        flat = (va[:, 0] == va[:, 1]) | (vb[:, 0] == vb[:, 1])
+        rel = np.abs(res[a][1] - res[b][1]) / np.maximum(np.abs(res[a][1]), 1e-3)
+        return (va == vb).all(1).mean(), (va.argmax(1) == vb.argmax(1))[~flat].mean(), np.percentile(rel, 99)
+    thr = BF16_SEARCH_AGREEMENT[name]
+    ident, action, p99 = agreement("tc32", "bf16")
+    assert ident >= thr["identical"] and action >= thr["same_action"] and p99 <= thr["value_p99"], \
+        f"{name}: bf16 vs tc32 identical {ident:.4f}, same action {action:.4f}, root value p99 {p99:.2e}"
+    # the two reference-precision modes differ only where a sub-1e-6 score tie flips
+    ident, action, p99 = agreement("fp32", "tc32")
+    assert ident >= 0.995 and action >= 0.999 and p99 <= 1e-4, \
+        f"{name}: tc32 vs fp32 identical {ident:.4f}, same action {action:.4f}, root value p99 {p99:.2e}"
