@@ -85,14 +85,26 @@ __device__ float normalise_policy(const Group<G>& g, float pol, int n) {
 
 // np.random.choice(n, bound, p=p, replace=False): returns the bit set of chosen indices and advances
 // the tree's uniform cursor by the number of draws numpy would have consumed.
+// numpy (mtrand.pyx, the replace=False branch) loops: draw m = bound - found uniforms, zero the found entries of p,
+// cdf = cumsum(p) / cumsum(p)[-1], new = searchsorted(cdf, x, 'right'), keep the not-yet-found values.  Which values a
+// round adds does not depend on the order of its draws (the result is sorted afterwards, mcts.py:208/:294), so the m
+// draws of a round are handled by m lanes at once: lane j generates uniform `cursor + j`, counts the cdf entries <= u
+// (searchsorted), and the new indices are OR-reduced over the group.  The cdf itself keeps numpy's sequential order of
+// additions.
 template <int G>
 __device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena& a, const SmzRng& rng, bool alive, int tree,
                                                float p32, int n, int bound, int& cursor) {
   unsigned found = 0;
   int nf = alive ? 0 : bound;
+  // np.random.choice validates p first ("probabilities contain NaN" / "are not non-negative"): ValueError in the reference
+  if (g.ballot(alive && g.gl < n && !(p32 >= 0.f))) {
+    if (alive) *a.error_flag = 2;
+    found = bound >= 32 ? 0xffffffffu : ((1u << bound) - 1u);
+    nf = bound;
+  }
   const double pd = (g.gl < n) ? (double)p32 : 0.0;
   for (int round = 0; __any_sync(FULL, nf < bound); ++round) {
-    if (round > 2 * SMZ_MAX_POLICY) {   // NaN / degenerate policy: numpy would raise; do not hang
+    if (round > 2 * SMZ_MAX_POLICY) {   // degenerate policy: do not hang
       if (nf < bound) {
         *a.error_flag = 2;
         for (int i = 0; i < n && nf < bound; ++i)
@@ -100,15 +112,22 @@ __device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena
       }
       break;
     }
-    const int m = bound - nf;                    // 0 for groups that are done
+    const int m = bound - nf;                    // 0 for groups that are done; m <= bound <= n <= G
     const double c = choice_cdf(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n);
-    for (int j = 0; __any_sync(FULL, j < m); ++j) {
-      const bool on = j < m;
-      const double u = on ? smz_rng_uniform(rng, tree, cursor + j) : 0.0;
-      int idx = __popc(g.ballot(c <= u));
-      idx = idx < n ? idx : n - 1;
-      if (on && !((found >> idx) & 1u)) { found |= 1u << idx; ++nf; }
+    const bool on = g.gl < m;
+    double u = 2.0;                              // lanes without a draw never match
+    if (__any_sync(FULL, on)) {
+      if (on) u = smz_rng_uniform(rng, tree, cursor + g.gl);
     }
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < G; ++i) cnt += g.bcast(c, i) <= u;      // cdf of lanes >= n is 2.0: never <= u < 1
+    const int idx = cnt < n ? cnt : n - 1;
+    unsigned bits = on ? (1u << idx) : 0u;
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) bits |= __shfl_xor_sync(FULL, bits, off, G);
+    found |= bits;
+    nf = alive ? __popc(found) : bound;
     cursor += m;
   }
   return found;
