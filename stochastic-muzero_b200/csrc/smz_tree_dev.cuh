@@ -67,12 +67,53 @@ __device__ float np_sum_f32(const Group<G>& g, float a, int n) {
 template <int G>
 __device__ double choice_cdf(const Group<G>& g, double p, int n) {
   double acc = 0.0, mine = 0.0;
+  if constexpr (G >= 16) {
+    // Wide groups: inclusive scan by doubling (log2 G steps instead of G).  A sum of float32-born values is usually
+    // EXACT in float64 (24-bit significands, 53 available), and exact partial sums do not depend on the order of the
+    // additions — so whenever every addition of the scan is exact (TwoSum error term zero), the scan equals numpy's
+    // sequential cumsum bit for bit.  Any inexact addition anywhere in the warp -> the sequential loop below.
+    double sc = p;
+    bool inexact = false;
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+      const double o = __shfl_up_sync(FULL, sc, off, G);
+      if (g.gl >= off) {
+        const double t = __dadd_rn(sc, o);
+        const double bv = __dsub_rn(t, sc);
+        const double err = __dadd_rn(__dsub_rn(sc, __dsub_rn(t, bv)), __dsub_rn(o, bv));
+        inexact |= err != 0.0;
+        sc = t;
+      }
+    }
+    if (!__any_sync(FULL, inexact)) {
+      acc = g.bcast(sc, G - 1);              // lanes >= n hold p = 0: the last lane carries the total
+      return (g.gl < n) ? __ddiv_rn(sc, acc) : 2.0;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < G; ++i) {
     acc = __dadd_rn(acc, g.bcast(p, i));     // + 0.0 beyond n leaves acc unchanged
     if (g.gl == i) mine = acc;
   }
   return (g.gl < n) ? __ddiv_rn(mine, acc) : 2.0;
+}
+
+// searchsorted(cdf, u, side='right') = #{i : cdf[i] <= u} for the non-decreasing cdf held one entry per lane
+// (lanes >= n hold 2.0); u may differ per lane.  The count never reaches G (cdf[n-1] = 1 > u, or 2.0 beyond n).
+template <int G>
+__device__ int searchsorted_right(const Group<G>& g, double c, double u) {
+  int cnt = 0;
+  if constexpr (G >= 16) {
+#pragma unroll
+    for (int step = G / 2; step >= 1; step >>= 1) {
+      const double cv = g.bcast(c, cnt + step - 1);
+      if (cv <= u) cnt += step;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < G; ++i) cnt += g.bcast(c, i) <= u;
+  }
+  return cnt;
 }
 
 // (policy + 1e-12) / sum in float32 (mcts.py:205-206, :291-292); lanes >= n hold 0.
@@ -119,9 +160,7 @@ __device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena
     if (__any_sync(FULL, on)) {
       if (on) u = smz_rng_uniform(rng, tree, cursor + g.gl);
     }
-    int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < G; ++i) cnt += g.bcast(c, i) <= u;      // cdf of lanes >= n is 2.0: never <= u < 1
+    const int cnt = searchsorted_right(g, c, u);               // cdf of lanes >= n is 2.0: never <= u < 1
     const int idx = cnt < n ? cnt : n - 1;
     unsigned bits = on ? (1u << idx) : 0u;
 #pragma unroll
@@ -407,9 +446,10 @@ __device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, cons
   // backup leaf -> root (mcts.py:299-308): lanes own path levels, the discounted return is a serial
   // float32 recurrence (mul then add, two roundings) carried through shuffles
   int2 root = make_int2(0, 0);
-  int n_chunks = (L + G - 1) / G;
+  int l_max = L;                                     // longest path in the warp
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) n_chunks = max(n_chunks, __shfl_xor_sync(FULL, n_chunks, off));
+  for (int off = 16; off > 0; off >>= 1) l_max = max(l_max, __shfl_xor_sync(FULL, l_max, off));
+  const int n_chunks = (l_max + G - 1) / G;
   for (int chunk = n_chunks - 1; chunk >= 0; --chunk) {
     const int l = chunk * G + g.gl;
     const bool valid = l < L;
@@ -419,12 +459,23 @@ __device__ __forceinline__ TreeState expand_backup_phase(const Group<G>& g, cons
     if (valid && l == L - 1 && branch) rec.w = __float_as_int(rew);
     const float r = __int_as_float(rec.w);
     float myv = 0.f;
+    if constexpr (G >= 16) {
+      // wide groups: paths are much shorter than G — walk only the levels some group of the warp has
+      for (int t = min(G, l_max - chunk * G) - 1; t >= 0; --t) {
+        const float ri = g.bcast(r, t);
+        if (chunk * G + t < L) {
+          if (g.gl == t) myv = v;
+          v = __fadd_rn(ri, __fmul_rn(a.discount, v));
+        }
+      }
+    } else {
 #pragma unroll
-    for (int t = G - 1; t >= 0; --t) {
-      const float ri = g.bcast(r, t);
-      if (chunk * G + t < L) {
-        if (g.gl == t) myv = v;
-        v = __fadd_rn(ri, __fmul_rn(a.discount, v));
+      for (int t = G - 1; t >= 0; --t) {
+        const float ri = g.bcast(r, t);
+        if (chunk * G + t < L) {
+          if (g.gl == t) myv = v;
+          v = __fadd_rn(ri, __fmul_rn(a.discount, v));
+        }
       }
     }
     if (valid) {
