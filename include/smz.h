@@ -44,6 +44,8 @@ enum {
   SMZ_NET_TC32 = 4,     /* fused tcgen05/TMEM MLP step at the reference's precision: every fp32 operand split into
                          * fp16 hi + lo, three products per K-step into one fp32 accumulator (1e-5 vs the reference,
                          * like SMZ_NET_FP32, at tensor-core speed); |activations| must stay below 65504            */
+  SMZ_NET_F16 = 5,      /* the same chain on plain fp16 operands (one product per K-step, fp32 accumulate): throughput
+                         * mode with 11-bit significands instead of bf16's 8; same range limit as SMZ_NET_TC32          */
   SMZ_NET_VISION = 3    /* vision (ResNet-v2, neural_network_vision_model.py) family, fp32 CUDA cores:
                          * obs_dim must be 3*98*98 (the reference fixes the model input, muzero_model.py:336),
                          * hidden state 3x7x7, state_dim/hidden_dim/num_hidden_layers = S/H/L of the MLP

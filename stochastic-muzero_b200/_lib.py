@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libsmz.so")
 
 SMZ_ABI_VERSION = 2
 SMZ_OK, SMZ_E_INVALID_ARG, SMZ_E_CUDA, SMZ_E_CAPACITY, SMZ_E_STATE = 0, -1, -2, -3, -4
-NET_EXTERNAL, NET_FP32, NET_BF16, NET_VISION, NET_TC32 = 0, 1, 2, 3, 4
+NET_EXTERNAL, NET_FP32, NET_BF16, NET_VISION, NET_TC32, NET_F16 = 0, 1, 2, 3, 4, 5
 RNG_PHILOX, RNG_TAPE = 0, 1
 
 

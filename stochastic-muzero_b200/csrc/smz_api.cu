@@ -56,7 +56,7 @@ struct smz_engine {
   float* img32_buf;
   float* blob_buf;
   SmzBf16Image* bf16;    // tcgen05 path state (null unless net_mode == SMZ_NET_BF16)
-  SmzTc32Image* tc32;    // fp32-grade tcgen05 path state (null unless net_mode == SMZ_NET_TC32)
+  SmzTc32Image* tc32;    // fp16-operand tcgen05 path state (null unless net_mode == SMZ_NET_TC32 / SMZ_NET_F16)
   SmzVisionImage* vision;  // vision family state (null unless net_mode == SMZ_NET_VISION)
   double* pbc_dev;
   double* rcp64_dev;
@@ -123,7 +123,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if (c.action_dim > SMZ_MAX_POLICY || c.chance_dim > SMZ_MAX_POLICY)
     return fail(SMZ_E_CAPACITY, "smz_create: policy width %d/%d exceeds %d (one lane per policy entry)",
                 c.action_dim, c.chance_dim, SMZ_MAX_POLICY);
-  if (c.net_mode < SMZ_NET_EXTERNAL || c.net_mode > SMZ_NET_TC32) return fail(SMZ_E_INVALID_ARG, "bad net_mode");
+  if (c.net_mode < SMZ_NET_EXTERNAL || c.net_mode > SMZ_NET_F16) return fail(SMZ_E_INVALID_ARG, "bad net_mode");
   if (c.net_mode == SMZ_NET_VISION) {
     if (c.obs_dim != 3 * 98 * 98) return fail(SMZ_E_INVALID_ARG, "smz_create: vision models take 3x98x98 observations (obs_dim %d)", c.obs_dim);
     if (c.action_dim != c.chance_dim) return fail(SMZ_E_INVALID_ARG, "smz_create: vision family needs chance_dim == action_dim");
@@ -186,7 +186,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 4 * B); ALLOC(a.rows4, 4 * B); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
   a.xin_q = c.net_mode == SMZ_NET_TC32 ? 16 : 8;
-  if (c.net_mode == SMZ_NET_BF16 || c.net_mode == SMZ_NET_TC32) { ALLOC(a.xin, 4 * B * a.xin_q); }
+  if (c.net_mode == SMZ_NET_BF16 || c.net_mode == SMZ_NET_TC32 || c.net_mode == SMZ_NET_F16) { ALLOC(a.xin, 4 * B * a.xin_q); }
   if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8); }
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
@@ -235,7 +235,8 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
     if (m != cudaSuccess) rc = fail(SMZ_E_CUDA, "memset: %s", cudaGetErrorString(m));
   }
   if (rc == SMZ_OK && c.net_mode == SMZ_NET_BF16) rc = smz_bf16_create(e->shape, a, &e->bf16, g_err, sizeof(g_err));
-  if (rc == SMZ_OK && c.net_mode == SMZ_NET_TC32) rc = smz_tc32_create(e->shape, &e->tc32, g_err, sizeof(g_err));
+  if (rc == SMZ_OK && (c.net_mode == SMZ_NET_TC32 || c.net_mode == SMZ_NET_F16))
+    rc = smz_tc32_create(e->shape, c.net_mode == SMZ_NET_F16 ? 1 : 3, &e->tc32, g_err, sizeof(g_err));
   if (rc == SMZ_OK && c.net_mode == SMZ_NET_VISION)
     rc = smz_vision_create(a.A, c.state_dim, c.hidden_dim, c.num_hidden_layers, &e->vision, g_err, sizeof(g_err));
   if (rc == SMZ_OK && cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking) != cudaSuccess)

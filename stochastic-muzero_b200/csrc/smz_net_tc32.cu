@@ -131,6 +131,15 @@ __device__ __forceinline__ unsigned char* a_at(unsigned char* part, int row, int
   return part + (col >> 3) * CHUNK_A + row * 16 + (col & 7) * 2;
 }
 
+__device__ __forceinline__ unsigned pack_f16(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const unsigned*>(&h);
+}
+// head-layer exponential: expf where the result feeds inverse_transform_with_support at reference precision, ex2.approx
+// in the plain-fp16 throughput mode
+template <bool PRECISE>
+__device__ __forceinline__ float exp_head(float x) { return PRECISE ? expf(x) : ex2f(x * 1.4426950408889634f); }
+
 // ELU (neural_network_mlp_model.py: nn.ELU).  exp through ex2.approx (relative error 2^-22: absolute error of
 // exp(x) - 1 below 2.4e-7); EXACT adds the degree-5 Taylor form of expm1 for -1/16 < x < 0, where the subtraction
 // would otherwise cancel.
@@ -149,9 +158,14 @@ __device__ __forceinline__ float elu32(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT>
+// NPROD = 3: fp32-grade (hi/lo split operands, three products).  NPROD = 1: plain fp16 operands (the hi parts only,
+// one product; "f16" throughput mode: 11-bit significands instead of bf16's 8, same speed class as the bf16 chain;
+// arena rows are then 64 fp16 = 128 B and the head exponentials use ex2.approx).
+template <int NPROD, bool EXACT>
 __global__ void __launch_bounds__(NTHR, 1)
 k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  constexpr bool SPLIT = NPROD == 3;
+  constexpr int ROWQ = SPLIT ? 16 : 8;            // 16-byte pieces per arena row
   extern __shared__ unsigned char smem_raw[];
   SmemT& sm = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -174,9 +188,9 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 
   auto load_weights = [&](int l) {
     const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;          // one part (hi or lo)
-    mbar_expect_tx(&sm.wbar[l & 1], 2 * bytes);
+    mbar_expect_tx(&sm.wbar[l & 1], (SPLIT ? 2 : 1) * bytes);
     bulk_g2s(sm.w[l & 1][0], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
-    bulk_g2s(sm.w[l & 1][1], ch.layer[l].w + (size_t)ch.layer[l].K * TN, bytes, &sm.wbar[l & 1]);
+    if (SPLIT) bulk_g2s(sm.w[l & 1][1], ch.layer[l].w + (size_t)ch.layer[l].K * TN, bytes, &sm.wbar[l & 1]);
   };
   if (tid == 0) {
     mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
@@ -209,8 +223,8 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     if (!is_issuer_warp) {
       const size_t ri = smz_row_index(a, sim, branch, min(tile * TM + srow, a.B - 1));
       const int4 rec = a.rows4[ri];           // {tree, parent slot, action, -}
-      h0 = a.xin[ri * 16 + skc];              // the descent copied the parent's row next to the record
-      l0 = a.xin[ri * 16 + 8 + skc];
+      h0 = a.xin[ri * ROWQ + skc];            // the descent copied the parent's row next to the record
+      if (SPLIT) l0 = a.xin[ri * ROWQ + 8 + skc];
       sidx = rec.x; sact = rec.z;
     }
     count = a.branch_count[sim * 2 + branch];
@@ -278,8 +292,10 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
               const unsigned long long oa = (unsigned long long)(k * ((2 * CHUNK_A) >> 4));
               const unsigned long long ow = (unsigned long long)(k * ((2 * CHUNK_W) >> 4));
               umma(d, ad_hi + oa, bd_hi + ow, k > 0 ? 1u : 0u);
-              umma(d, ad_lo + oa, bd_hi + ow, 1u);
-              umma(d, ad_hi + oa, bd_lo + ow, 1u);
+              if (SPLIT) {
+                umma(d, ad_lo + oa, bd_hi + ow, 1u);
+                umma(d, ad_hi + oa, bd_lo + ow, 1u);
+              }
             }
         }
         __syncwarp();
@@ -298,11 +314,11 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       const bool valid = tile * TM + srow < count;
       const uint4 z = make_uint4(0, 0, 0, 0);
       sts16(sm.a[0] + skc * CHUNK_A + srow * 16, valid ? h0 : z);
-      sts16(sm.a[1] + skc * CHUNK_A + srow * 16, valid ? l0 : z);
+      if (SPLIT) sts16(sm.a[1] + skc * CHUNK_A + srow * 16, valid ? l0 : z);
       if (job.input_kind == IN_OBS) {
         if ((skc + 8) * 8 < ch.kin) {
           sts16(sm.a[0] + (skc + 8) * CHUNK_A + srow * 16, valid ? h1 : z);
-          sts16(sm.a[1] + (skc + 8) * CHUNK_A + srow * 16, valid ? l1 : z);
+          if (SPLIT) sts16(sm.a[1] + (skc + 8) * CHUNK_A + srow * 16, valid ? l1 : z);
         }
       } else if (skc < ch.onehot_pad / 8) {              // one-hot action / code: a single fp16 1.0 in the hi part
         const int act = valid ? sact : -1;
@@ -312,7 +328,7 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           w4[j >> 1] = (j & 1) ? 0x3C000000u : 0x00003C00u;
         }
         sts16(sm.a[0] + (8 + skc) * CHUNK_A + srow * 16, make_uint4(w4[0], w4[1], w4[2], w4[3]));
-        sts16(sm.a[1] + (8 + skc) * CHUNK_A + srow * 16, z);
+        if (SPLIT) sts16(sm.a[1] + (8 + skc) * CHUNK_A + srow * 16, z);
       }
       if (skc == 0) sm.rowidx[srow] = valid ? sidx : -1;
     }
@@ -349,10 +365,15 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             const float a0 = elu32<EXACT>(fmaf(__uint_as_float(rr[0]), isc, bi.x)), a1 = elu32<EXACT>(fmaf(__uint_as_float(rr[1]), isc, bi.y));
             const float b0 = elu32<EXACT>(fmaf(__uint_as_float(rr[2]), isc, bi.x)), b1 = elu32<EXACT>(fmaf(__uint_as_float(rr[3]), isc, bi.y));
             unsigned hi, lo;
-            split2(a0, a1, hi, lo);
-            sts4(a_at(sm.a[0], rA, col), hi); sts4(a_at(sm.a[1], rA, col), lo);
-            split2(b0, b1, hi, lo);
-            sts4(a_at(sm.a[0], rB, col), hi); sts4(a_at(sm.a[1], rB, col), lo);
+            if (SPLIT) {
+              split2(a0, a1, hi, lo);
+              sts4(a_at(sm.a[0], rA, col), hi); sts4(a_at(sm.a[1], rA, col), lo);
+              split2(b0, b1, hi, lo);
+              sts4(a_at(sm.a[0], rB, col), hi); sts4(a_at(sm.a[1], rB, col), lo);
+            } else {
+              sts4(a_at(sm.a[0], rA, col), pack_f16(a0, a1));
+              sts4(a_at(sm.a[0], rB, col), pack_f16(b0, b1));
+            }
           }
           fence_async_smem();
           if (c == 1) tc_fence_before();
@@ -424,10 +445,16 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             const int col = c0 + g * 8 + cq;
             const float a0 = __fdiv_rn(xa[2 * g] - loa, sa), a1 = __fdiv_rn(xa[2 * g + 1] - loa, sa);
             const float b0 = __fdiv_rn(xb[2 * g] - lob, sb), b1 = __fdiv_rn(xb[2 * g + 1] - lob, sb);
-            split2(a0, a1, pend_ah[g], pend_al[g]);
-            split2(b0, b1, pend_bh[g], pend_bl[g]);
-            sts4(a_at(sm.a[0], rA, col), pend_ah[g]); sts4(a_at(sm.a[1], rA, col), pend_al[g]);
-            sts4(a_at(sm.a[0], rB, col), pend_bh[g]); sts4(a_at(sm.a[1], rB, col), pend_bl[g]);
+            if (SPLIT) {
+              split2(a0, a1, pend_ah[g], pend_al[g]);
+              split2(b0, b1, pend_bh[g], pend_bl[g]);
+              sts4(a_at(sm.a[1], rA, col), pend_al[g]);
+              sts4(a_at(sm.a[1], rB, col), pend_bl[g]);
+            } else {
+              pend_ah[g] = pack_f16(a0, a1); pend_bh[g] = pack_f16(b0, b1);
+            }
+            sts4(a_at(sm.a[0], rA, col), pend_ah[g]);
+            sts4(a_at(sm.a[0], rB, col), pend_bh[g]);
             if (job.hidden_dst) {
               if (idxA >= 0) *reinterpret_cast<float2*>(job.hidden_dst + (size_t)idxA * SMZ_SP + col) = make_float2(a0, a1);
               if (idxB >= 0) *reinterpret_cast<float2*>(job.hidden_dst + (size_t)idxB * SMZ_SP + col) = make_float2(b0, b1);
@@ -443,7 +470,7 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const float pos = (float)(((c0 + g * 8 + cq + j) & 63) - S / 2);
-              const float ea = expf(xa[2 * g + j] - ma), eb = expf(xb[2 * g + j] - mb);     // padded logits sit at -1e30: e == 0
+              const float ea = exp_head<SPLIT>(xa[2 * g + j] - ma), eb = exp_head<SPLIT>(xb[2 * g + j] - mb);   // padded logits sit at -1e30: e == 0
               za += ea; ya = fmaf(pos, ea, ya);
               zb += eb; yb = fmaf(pos, eb, yb);
             }
@@ -493,8 +520,8 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           float za = 0.f, zb = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            xa[i] = expf(xa[i] - ma); za += xa[i];
-            xb[i] = expf(xb[i] - mb); zb += xb[i];
+            xa[i] = exp_head<SPLIT>(xa[i] - ma); za += xa[i];
+            xb[i] = exp_head<SPLIT>(xb[i] - mb); zb += xb[i];
           }
 #pragma unroll
           for (int off = 1; off <= 2; off <<= 1) {
@@ -528,14 +555,14 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           for (int g = 0; g < 4; ++g) {
             const int col = c0 + g * 8 + cq;
             if (idxA >= 0) {
-              __half* row = job.hidden_split_dst + (size_t)idxA * (2 * SMZ_SP);
+              __half* row = job.hidden_split_dst + (size_t)idxA * (ROWQ * 8);
               *reinterpret_cast<unsigned*>(row + col) = pend_ah[g];
-              *reinterpret_cast<unsigned*>(row + SMZ_SP + col) = pend_al[g];
+              if (SPLIT) *reinterpret_cast<unsigned*>(row + SMZ_SP + col) = pend_al[g];
             }
             if (idxB >= 0) {
-              __half* row = job.hidden_split_dst + (size_t)idxB * (2 * SMZ_SP);
+              __half* row = job.hidden_split_dst + (size_t)idxB * (ROWQ * 8);
               *reinterpret_cast<unsigned*>(row + col) = pend_bh[g];
-              *reinterpret_cast<unsigned*>(row + SMZ_SP + col) = pend_bl[g];
+              if (SPLIT) *reinterpret_cast<unsigned*>(row + SMZ_SP + col) = pend_bl[g];
             }
           }
         }
@@ -608,12 +635,12 @@ __global__ void k_copy_f32(float* __restrict__ dst, const float* __restrict__ sr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
-__global__ void k_split_to_f32(float* __restrict__ dst, const __half* __restrict__ src, int n_rows) {
+__global__ void k_split_to_f32(float* __restrict__ dst, const __half* __restrict__ src, int n_rows, int row_halves) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * SMZ_SP) return;
   const int r = i / SMZ_SP, c = i % SMZ_SP;
-  const __half* row = src + (size_t)r * 2 * SMZ_SP;
-  dst[i] = __half2float(row[c]) + __half2float(row[SMZ_SP + c]);
+  const __half* row = src + (size_t)r * row_halves;
+  dst[i] = __half2float(row[c]) + (row_halves > SMZ_SP ? __half2float(row[SMZ_SP + c]) : 0.f);
 }
 
 }  // namespace
@@ -639,11 +666,12 @@ struct SmzTc32Image {
   float* scales;           // device [18][2]
   int smem_bytes;
   int exact_elu;
+  int nprod;               // 3: fp32-grade split operands (SMZ_NET_TC32); 1: plain fp16 operands (SMZ_NET_F16)
 };
 
 static int round16(int v) { return (v + 15) / 16 * 16; }
 
-int smz_tc32_create(const SmzNetShape& sh, SmzTc32Image** out, char* err, size_t err_len) {
+int smz_tc32_create(const SmzNetShape& sh, int nprod, SmzTc32Image** out, char* err, size_t err_len) {
   if (2 * (sh.L + 2) > MAXL) {
     snprintf(err, err_len, "SMZ_NET_TC32: number_of_hidden_layer %d exceeds %d", sh.L, MAXL / 2 - 2);
     return SMZ_E_CAPACITY;
@@ -686,9 +714,11 @@ int smz_tc32_create(const SmzNetShape& sh, SmzTc32Image** out, char* err, size_t
   }
   im->bias_pool = (float*)p;
   im->smem_bytes = (int)sizeof(SmemT) + 1024;
-  im->exact_elu = getenv("SMZ_TC32_POLY") ? atoi(getenv("SMZ_TC32_POLY")) : 0;
-  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
-  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  im->nprod = nprod == 1 ? 1 : 3;
+  im->exact_elu = (im->nprod == 3 && getenv("SMZ_TC32_POLY")) ? atoi(getenv("SMZ_TC32_POLY")) : 0;
+  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
   *out = im;
   return SMZ_OK;
 }
@@ -799,13 +829,15 @@ int smz_tc32_pack(SmzTc32Image* im, const SmzNetShape& sh, const float* blob, cu
 
 void smz_tc32_read_hidden(const SmzArena& a, int slot, int n_trees, float* out, cudaStream_t s) {
   const int n = n_trees * SMZ_SP;
-  k_split_to_f32<<<(n + 255) / 256, 256, 0, s>>>(out, reinterpret_cast<const __half*>(a.hidden) + (size_t)slot * a.B * 2 * SMZ_SP, n_trees);
+  const int row_halves = a.xin_q * 8;           // 128: [hi | lo], 64: plain fp16
+  k_split_to_f32<<<(n + 255) / 256, 256, 0, s>>>(out, reinterpret_cast<const __half*>(a.hidden) + (size_t)slot * a.B * row_halves,
+                                                 n_trees, row_halves);
 }
 
 static void launch(SmzTc32Image* im, dim3 grid, cudaStream_t s, bool pdl, const SmzArena& a, const Chain& c0, const Chain& c1,
                    Job job, int sim) {
   job.exact_elu = im->exact_elu;
-  auto* k = im->exact_elu ? k_tc32_chain_m64<true> : k_tc32_chain_m64<false>;
+  auto* k = im->nprod == 1 ? k_tc32_chain_m64<1, false> : (im->exact_elu ? k_tc32_chain_m64<3, true> : k_tc32_chain_m64<3, false>);
   smz_launch(k, grid, dim3(NTHR), (size_t)im->smem_bytes, s, pdl, a, c0, c1, job, sim);
 }
 
@@ -820,7 +852,7 @@ void smz_tc32_root(SmzTc32Image* im, const SmzArena& a, const SmzNetShape& sh, i
 void smz_tc32_sim(SmzTc32Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, int sim, bool pdl, cudaStream_t s) {
   Job job{};
   job.input_kind = IN_GATHER; job.n_rows = n_trees; job.S = sh.S;
-  job.hidden_split_dst = reinterpret_cast<__half*>(a.hidden) + (size_t)(sim + 1) * a.B * 2 * SMZ_SP;
+  job.hidden_split_dst = reinterpret_cast<__half*>(a.hidden) + (size_t)(sim + 1) * a.B * (a.xin_q * 8);
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   launch(im, dim3(2 * ((n_trees + TM - 1) / TM)), s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
 }

@@ -7,7 +7,8 @@
 
 struct SmzTc32Image;
 
-int smz_tc32_create(const SmzNetShape& sh, SmzTc32Image** out, char* err, size_t err_len);
+// nprod 3: fp32-grade (hi/lo split, three products; SMZ_NET_TC32); nprod 1: plain fp16 operands (SMZ_NET_F16)
+int smz_tc32_create(const SmzNetShape& sh, int nprod, SmzTc32Image** out, char* err, size_t err_len);
 void smz_tc32_destroy(SmzTc32Image* im);
 int smz_tc32_pack(SmzTc32Image* im, const SmzNetShape& sh, const float* blob_dev, cudaStream_t s, char* err, size_t err_len);
 void smz_tc32_root(SmzTc32Image* im, const SmzArena& a, const SmzNetShape& sh, int n_trees, const float* obs, cudaStream_t s);

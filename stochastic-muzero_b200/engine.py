@@ -17,7 +17,7 @@ from .weights import VISION_FLAT, ModelShape, VisionShape
 SEARCH_KEYS = ("pb_c_base", "pb_c_init", "discount", "root_dirichlet_alpha", "root_exploration_fraction",
                "num_simulations", "maxium_action_sample", "number_of_player", "custom_loop")
 _NET = {"external": _lib.NET_EXTERNAL, "fp32": _lib.NET_FP32, "bf16": _lib.NET_BF16, "vision": _lib.NET_VISION,
-        "tc32": _lib.NET_TC32}
+        "tc32": _lib.NET_TC32, "f16": _lib.NET_F16}
 _RNG = {"philox": _lib.RNG_PHILOX, "tape": _lib.RNG_TAPE}
 
 

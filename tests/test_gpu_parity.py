@@ -182,6 +182,56 @@ def test_bf16_tcgen05_network_step_within_stated_tolerance(name):
         e.close()
 
 
+# plain fp16 operands (11-bit significands, fp32 accumulate, fp32 epilogue): measured worst case on these fixtures
+# hidden 1.8e-4, policy 5.4e-5, value 4.0e-3 at |value| = 34 (relative 1.2e-4) — about 8x tighter than bf16
+F16_HIDDEN_ATOL = 1e-3
+F16_POLICY_ATOL = 5e-4
+F16_SCALAR_TOL = dict(atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("name", golden_io.net_cases())
+def test_f16_tcgen05_network_step_within_stated_tolerance(name):
+    z = golden_io.load_net_case(name)
+    eng = _net_engine(z, B=256, net="f16")
+    h = dict(atol=F16_HIDDEN_ATOL, rtol=0)
+    p = dict(atol=F16_POLICY_ATOL, rtol=0)
+    np.testing.assert_allclose(eng.net_eval("repr", z["obs"])["hidden"].cpu().numpy(), z["repr_h"], **h)
+    o = eng.net_eval("pred", z["repr_h"])
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["pred_policy"], **p)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["pred_value"], **F16_SCALAR_TOL)
+    np.testing.assert_allclose(eng.net_eval("adyn", z["repr_h"], z["actions"])["hidden"].cpu().numpy(), z["adyn_h"], **h)
+    o = eng.net_eval("apred", z["adyn_h"])
+    np.testing.assert_allclose(o["policy"].cpu().numpy(), z["apred_policy"], **p)
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z["apred_value"], **F16_SCALAR_TOL)
+    o = eng.net_eval("dyn", z["adyn_h"], z["actions"])
+    np.testing.assert_allclose(o["hidden"].cpu().numpy(), z["dyn_h"], **h)
+    np.testing.assert_allclose(o["reward"].cpu().numpy(), z["dyn_reward"], **F16_SCALAR_TOL)
+    o = eng.net_eval("enc", z["obs"])
+    np.testing.assert_allclose(o["probs"].cpu().numpy(), z["enc_probs"], **p)
+    eng.close()
+
+
+@pytest.mark.parametrize("net", ["bf16", "f16", "tc32"])
+def test_tensor_core_search_is_self_consistent_with_the_oracle(net):
+    """Every tensor-core mode end to end (device Philox, ragged last tile): the tree statistics are the reference
+    algorithm's, bit for bit, on the network outputs the engine actually produced."""
+    zn = golden_io.load_net_case("ckpt450")
+    B, N, seed = 300, 50, 99
+    eng = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=seed, record=True)
+    obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(1))
+    eng.root(obs=obs, train=True)
+    eng.simulate(N)
+    eng.stats()
+    rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+    cfg = O.SearchConfig(discount=0.997, num_simulations=N, maxium_action_sample=2)
+    for b in (0, 63, 64, 127, 128, 255, 256, 299):
+        model = O.TapeModel(rec["root_policy"][b, :2], rec["sim_policy"][b], np.full(N, 2), rec["sim_value"][b],
+                            rec["sim_reward"][b])
+        tree = O.search(cfg, model, O.PhiloxUniforms(seed, b), train=True, dirichlet=rec["dirichlet"][b])
+        golden_io.assert_dump_equal(eng.export_tree(b), tree.dump(), f"{net}[{b}]")
+    eng.close()
+
+
 def test_bf16_search_is_self_consistent_with_the_oracle():
     """Throughput mode end to end: device Philox + bf16 network.  The tree statistics must still be
     the reference algorithm's, bit for bit, on the network outputs the engine actually produced."""
@@ -711,14 +761,14 @@ def test_partial_batch_equals_exact_size_engine():
     obs = torch.randn(77, 4, generator=torch.Generator().manual_seed(9))
     out = []
     for cap in (77, 300):
-        for net in ("fp32", "bf16", "tc32"):
+        for net in ("fp32", "bf16", "tc32", "f16"):
             e = _net_engine(zn, B=cap, N=20, net=net, rng="philox", seed=66)
             e.root(obs=obs, train=True); e.simulate(20)
             r = e.read_roots()
             assert r["visits"].shape == (77, 2)
             out.append((net, r["visits"].cpu().numpy(), r["root_values"].cpu().numpy()))
             e.close()
-    for net in ("fp32", "bf16", "tc32"):
+    for net in ("fp32", "bf16", "tc32", "f16"):
         a, b = [o for o in out if o[0] == net]
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), f"{net}: capacity changed the result"
 
@@ -901,7 +951,7 @@ def test_launch_counters_and_real_tree_step_hook():
     zn = golden_io.load_net_case("mlp450_seed0")
     B, N = 200, 12
     obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(5))
-    for net in ("fp32", "bf16", "tc32"):
+    for net in ("fp32", "bf16", "tc32", "f16"):
         a = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=8)
         a.root(obs=obs, train=True); a.simulate(N)
         st = a.stats()
@@ -1026,6 +1076,9 @@ def test_full_size_config4_65536_trees_50_simulations():
 # Measured on B200 (tools/diag_bf16_agreement.py): random init 0.9998 / 1.0000 / 0; checkpoint 450 0.908 / 0.993 / 1.5e-2.
 BF16_SEARCH_AGREEMENT = {"mlp450_seed0": dict(identical=0.99, same_action=0.999, value_p99=1e-3),
                          "ckpt450": dict(identical=0.85, same_action=0.98, value_p99=3e-2)}
+# the plain-fp16 mode: random init 1.0000 / 1.0000 / 0; checkpoint 450 0.9875 / 0.998 / 6.6e-3
+F16_SEARCH_AGREEMENT = {"mlp450_seed0": dict(identical=0.995, same_action=0.999, value_p99=1e-3),
+                        "ckpt450": dict(identical=0.97, same_action=0.99, value_p99=1.5e-2)}
 
 
 @pytest.mark.parametrize("name", sorted(BF16_SEARCH_AGREEMENT))
@@ -1034,7 +1087,7 @@ def test_bf16_search_result_fidelity_against_reference_precision(name):
     B, N = 4096, 50
     obs = torch.randn(B, 4, generator=torch.Generator().manual_seed(0)) * 0.1
     res = {}
-    for net in ("fp32", "tc32", "bf16"):
+    for net in ("fp32", "tc32", "bf16", "f16"):
         eng = _net_engine(zn, B=B, N=N, net=net, rng="philox", seed=11)
         eng.root(obs=obs, train=True); eng.simulate(N)
         r = eng.read_roots()
@@ -1047,10 +1100,11 @@ def test_bf16_search_result_fidelity_against_reference_precision(name):
         flat = (va[:, 0] == va[:, 1]) | (vb[:, 0] == vb[:, 1])
         rel = np.abs(res[a][1] - res[b][1]) / np.maximum(np.abs(res[a][1]), 1e-3)
         return (va == vb).all(1).mean(), (va.argmax(1) == vb.argmax(1))[~flat].mean(), np.percentile(rel, 99)
-    thr = BF16_SEARCH_AGREEMENT[name]
-    ident, action, p99 = agreement("tc32", "bf16")
-    assert ident >= thr["identical"] and action >= thr["same_action"] and p99 <= thr["value_p99"], \
-        f"{name}: bf16 vs tc32 identical {ident:.4f}, same action {action:.4f}, root value p99 {p99:.2e}"
+    for mode, table in (("bf16", BF16_SEARCH_AGREEMENT), ("f16", F16_SEARCH_AGREEMENT)):
+        thr = table[name]
+        ident, action, p99 = agreement("tc32", mode)
+        assert ident >= thr["identical"] and action >= thr["same_action"] and p99 <= thr["value_p99"], \
+            f"{name}: {mode} vs tc32 identical {ident:.4f}, same action {action:.4f}, root value p99 {p99:.2e}"
     # the two reference-precision modes differ only where a sub-1e-6 score tie flips
     ident, action, p99 = agreement("fp32", "tc32")
     assert ident >= 0.995 and action >= 0.999 and p99 <= 1e-4, \
