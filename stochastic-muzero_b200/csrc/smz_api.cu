@@ -71,7 +71,7 @@ struct smz_engine {
   int64_t launches;        // kernels of the last smz_root + smz_simulate
   int64_t launches_total;  // kernels since smz_create
   cudaGraphExec_t graph_exec;
-  int graph_trees, graph_sims, graph_first;
+  int graph_trees, graph_sims, graph_first, graph_launches;
   cudaStream_t capture_stream;
   int use_pdl, use_fused_tree, use_mega;
 };
@@ -238,7 +238,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   if (rc == SMZ_OK && (c.net_mode == SMZ_NET_TC32 || c.net_mode == SMZ_NET_F16))
     rc = smz_tc32_create(e->shape, c.net_mode == SMZ_NET_F16 ? 1 : 3, &e->tc32, g_err, sizeof(g_err));
   if (rc == SMZ_OK && c.net_mode == SMZ_NET_VISION)
-    rc = smz_vision_create(a.A, c.state_dim, c.hidden_dim, c.num_hidden_layers, &e->vision, g_err, sizeof(g_err));
+    rc = smz_vision_create(a.A, c.state_dim, c.hidden_dim, c.num_hidden_layers, c.max_trees, &e->vision, g_err, sizeof(g_err));
   if (rc == SMZ_OK && cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = fail(SMZ_E_CUDA, "cudaStreamCreate failed");
   if (rc != SMZ_OK) { smz_destroy(e); return rc; }
@@ -409,11 +409,13 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32
   return SMZ_OK;
 }
 
-static void enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false, int tree_mode = 0) {
-  if (e->vision) smz_vision_sim(e->vision, e->a, e->n_trees, sim, s);
-  else if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, tree_mode, s);
+// returns the number of kernels launched
+static int enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false, int tree_mode = 0) {
+  if (e->vision) return smz_vision_sim(e->vision, e->a, e->n_trees, sim, s);
+  if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, tree_mode, s);
   else if (e->tc32) smz_tc32_sim(e->tc32, e->a, e->shape, e->n_trees, sim, pdl, s);
   else smz_net_f32_sim(e->a, e->shape, e->img32, e->n_trees, sim, s);
+  return 1;
 }
 
 int smz_net_step(smz_engine* e, int32_t sim, void* stream) {
@@ -422,8 +424,7 @@ int smz_net_step(smz_engine* e, int32_t sim, void* stream) {
   if (e->cfg.net_mode == SMZ_NET_EXTERNAL) return fail(SMZ_E_STATE, "smz_net_step: engine has no internal network");
   if (!e->have_weights) return fail(SMZ_E_STATE, "smz_net_step: smz_set_weights has not been called");
   ON_DEVICE(e);
-  enqueue_net(e, sim, (cudaStream_t)stream);
-  count_launches(e, 1);
+  count_launches(e, enqueue_net(e, sim, (cudaStream_t)stream));
   CU(cudaGetLastError());
   return SMZ_OK;
 }
@@ -456,7 +457,8 @@ int smz_backup_select(smz_engine* e, int32_t sim, void* stream) {
   return SMZ_OK;
 }
 
-static void enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
+// returns the number of kernels enqueued
+static int enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   const SmzArena& a = e->a;
   const int G = e->cfg.lanes_per_tree;
   // select(first); then per simulation: network step, then [expand+backup(sim) fused with select(sim+1)]
@@ -464,16 +466,18 @@ static void enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   // next kernel's CTAs become resident and run their prologue while the previous one drains.
   const bool pdl = (e->bf16 != nullptr || e->tc32 != nullptr) && e->use_pdl;
   smz_launch_select(a, G, e->n_trees, first, nullptr, nullptr, nullptr, s);
+  int launched = 1;
   // tensor-core network + 4 lanes per tree: the tree phases run in the tail of the network kernel (one launch
   // per simulation); otherwise a second, fused tree kernel follows each network step
   const bool fuse = e->bf16 != nullptr && G == 4 && e->use_fused_tree;
   for (int sim = first; sim < first + n_sims; ++sim) {
     const bool last = sim + 1 >= first + n_sims;
-    if (fuse) { enqueue_net(e, sim, s, pdl, last ? 1 : 2); continue; }
-    enqueue_net(e, sim, s, pdl);
+    if (fuse) { launched += enqueue_net(e, sim, s, pdl, last ? 1 : 2); continue; }
+    launched += enqueue_net(e, sim, s, pdl) + 1;
     if (!last) smz_launch_backup_select(a, G, e->n_trees, sim, pdl, s);
     else smz_launch_expand_backup(a, G, e->n_trees, sim, a.out_policy, a.W, a.out_value, a.out_reward, s);
   }
+  return launched;
 }
 
 int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
@@ -501,7 +505,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     drop_graph(e);
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_sims(e, first, n_sims, e->capture_stream);
+    e->graph_launches = enqueue_sims(e, first, n_sims, e->capture_stream);
     cudaError_t ce = cudaStreamEndCapture(e->capture_stream, &graph);
     if (ce == cudaSuccess) {
       ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
@@ -518,7 +522,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
     e->graph_trees = e->n_trees; e->graph_sims = n_sims; e->graph_first = first;
   }
   CU(cudaGraphLaunch(e->graph_exec, s));
-  count_launches(e, ((e->bf16 && e->cfg.lanes_per_tree == 4 && e->use_fused_tree) ? 1LL : 2LL) * n_sims + 1);
+  count_launches(e, e->graph_launches);
   e->sims_done += n_sims;
   return SMZ_OK;
 }

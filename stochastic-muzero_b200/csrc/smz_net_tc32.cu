@@ -37,7 +37,8 @@ constexpr int KMAX = 128;               // widest K
 constexpr int MAXL = 24;                // layers per chain: 2 * (L + 2), L <= 10
 constexpr int NEPI = 512;               // 16 epilogue warps: 4 TMEM lane quarters x 4 column blocks
 constexpr int NTHR = NEPI + 32;         // + issuer warp
-constexpr int A_BYTES = TM * KMAX * 2;  // 16 KB per operand part
+constexpr int KVIS = 160;               // widest first layer: the 147 features of a vision head, padded
+constexpr int A_BYTES = TM * KMAX * 2;  // 16 KB per operand part (MLP family)
 constexpr int W_BYTES = TN * KMAX * 2;  // 32 KB per operand part
 constexpr int CHUNK_A = TM * 16;        // bytes between K-chunks (8 halves) of the A operand: LBO
 constexpr int CHUNK_W = TN * 16;
@@ -47,7 +48,9 @@ constexpr int R0 = 96;                  // columns of the first hidden-layer rou
 constexpr unsigned IDESC = (1u << 4) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
 
 enum LayerKind { LK_HIDDEN = 0, LK_STATE = 1, LK_STATE_REWARD = 2, LK_PRED = 3, LK_CODE = 4 };
-enum InputKind { IN_GATHER = 0, IN_OBS = 1, IN_ROWS = 2 };
+// IN_FEAT: the MLP heads of the vision family (neural_network_vision_model.py: 147 -> H -> .. -> S / A after the 1x1
+// convolutions).  Rows = the compacted leaves of a simulation, features written by k_vision_step's convolution stage.
+enum InputKind { IN_GATHER = 0, IN_OBS = 1, IN_ROWS = 2, IN_FEAT = 3 };
 
 struct LayerRef {
   const __half* w;          // [hi | lo], each [K/8][128][8] canonical K-major image of W * 2^s
@@ -80,11 +83,16 @@ struct Job {
   int pstride;
   int S;
   int exact_elu;            // 1: polynomial expm1 for small |x| next to ex2.approx (SMZ_TC32_POLY=1)
+  // IN_FEAT: CTAs [c*T, (c+1)*T) serve combination c of (branch, head): 0 afterstate value, 1 afterstate policy,
+  // 2 dynamics reward, 3 dynamics value, 4 dynamics policy — chain `vchains[c]` (device memory)
+  const float* feat;        // [3 heads: reward, value, policy][2 branches][B rows][KVIS] fp32
+  const Chain* vchains;
 };
 
+template <int KA>           // widest K of the chain: 128 (MLP family) or 160 (vision heads)
 struct SmemT {
-  alignas(1024) unsigned char a[2][A_BYTES];        // activations: hi, lo
-  alignas(1024) unsigned char w[2][2][W_BYTES];     // weights: [ring slot][hi, lo]
+  alignas(1024) unsigned char a[2][TM * KA * 2];    // activations: hi, lo
+  alignas(1024) unsigned char w[2][2][TN * KA * 2]; // weights: [ring slot][hi, lo]
   float bias[MAXL][TN];
   unsigned long long wbar[2];
   unsigned long long dbar[2];
@@ -157,17 +165,21 @@ __device__ __forceinline__ float elu32(float x) {
   return x > 0.f ? x : r;
 }
 
+template <bool EXACT, bool RELU>
+__device__ __forceinline__ float act32(float x) { return RELU ? fmaxf(x, 0.f) : elu32<EXACT>(x); }
+
 // ---------------------------------------------------------------------------------------------
 // NPROD = 3: fp32-grade (hi/lo split operands, three products).  NPROD = 1: plain fp16 operands (the hi parts only,
 // one product; "f16" throughput mode: 11-bit significands instead of bf16's 8, same speed class as the bf16 chain;
 // arena rows are then 64 fp16 = 128 B and the head exponentials use ex2.approx).
-template <int NPROD, bool EXACT>
+// RELU: the vision heads use nn.ReLU between their Linear layers (the MLP family nn.ELU).
+template <int NPROD, bool EXACT, bool RELU, int KA>
 __global__ void __launch_bounds__(NTHR, 1)
 k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   constexpr bool SPLIT = NPROD == 3;
   constexpr int ROWQ = SPLIT ? 16 : 8;            // 16-byte pieces per arena row
   extern __shared__ unsigned char smem_raw[];
-  SmemT& sm = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SmemT<KA>& sm = *reinterpret_cast<SmemT<KA>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer_warp = warp == NEPI / 32;
   const int q = warp & 3;                  // TMEM lane quarter: tile rows 16q .. 16q+15
@@ -177,13 +189,25 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 
   // gather launches use a static split: CTAs [0, T) serve the afterstate rows, [T, 2T) the dynamics rows, so the
   // weight chain is known before the previous kernel has finished
-  int tile = blockIdx.x, branch = 0;
+  int tile = blockIdx.x, branch = 0, head = 1;
+  const Chain* chp = &chain0;
+  float *value_dst = job.value_dst, *policy_dst = job.policy_dst;
   if (job.input_kind == IN_GATHER) {
     const int T = (job.n_rows + TM - 1) / TM;
     branch = tile >= T;
     tile -= branch * T;
+    if (branch) chp = &chain1;
+  } else if (job.input_kind == IN_FEAT) {
+    const int T = (job.n_rows + TM - 1) / TM;
+    const int combo = tile / T;
+    tile -= combo * T;
+    branch = combo >= 2;
+    head = combo == 2 ? 0 : (combo == 0 || combo == 3 ? 1 : 2);      // 0 reward, 1 value, 2 policy
+    chp = job.vchains + combo;
+    if (head == 0) value_dst = job.reward_dst;                        // the reward head is a value-shaped head
+    if (head != 2) policy_dst = nullptr;
   }
-  const Chain& ch = branch ? chain1 : chain0;
+  const Chain& ch = *chp;
   const int nl = ch.n_layers;
 
   auto load_weights = [&](int l) {
@@ -217,7 +241,7 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   //      wide observations); requested before the row count of the branch is known ------------------------------
   const int srow = tid & 63, skc = (tid >> 6) & 7;
   int sidx = -1, sact = -1;                   // output index and one-hot position of the staged row
-  uint4 h0 = make_uint4(0, 0, 0, 0), l0 = h0, h1 = h0, l1 = h0;
+  uint4 h0 = make_uint4(0, 0, 0, 0), l0 = h0, h1 = h0, l1 = h0, h2 = h0, l2 = h0;
   int count = job.n_rows;
   if (job.input_kind == IN_GATHER) {
     if (!is_issuer_warp) {
@@ -226,6 +250,23 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       h0 = a.xin[ri * ROWQ + skc];            // the descent copied the parent's row next to the record
       if (SPLIT) l0 = a.xin[ri * ROWQ + 8 + skc];
       sidx = rec.x; sact = rec.z;
+    }
+    count = a.branch_count[sim * 2 + branch];
+  } else if (job.input_kind == IN_FEAT) {
+    if (!is_issuer_warp) {
+      const int row = min(tile * TM + srow, a.B - 1);
+      sidx = a.rows4[smz_row_index(a, sim, branch, row)].x;
+      const float* src = job.feat + ((size_t)(head * 2 + branch) * a.B + row) * KVIS;
+      float v[8];
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const int kc = skc + 8 * part;
+        if (kc * 8 < KVIS) {
+          const float4 lo4 = *reinterpret_cast<const float4*>(src + kc * 8), hi4 = *reinterpret_cast<const float4*>(src + kc * 8 + 4);
+          v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
+          if (part == 0) split8(v, h0, l0); else if (part == 1) split8(v, h1, l1); else split8(v, h2, l2);
+        }
+      }
     }
     count = a.branch_count[sim * 2 + branch];
   } else if (!is_issuer_warp) {
@@ -287,8 +328,8 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k >= (c ? R0 / 16 : 0) && k < (c ? 8 : R0 / 16) && k < nk) {
+          for (int k = 0; k < KA / 16; ++k)
+            if (k >= (c ? R0 / 16 : 0) && k < (c ? KA / 16 : R0 / 16) && k < nk) {
               const unsigned long long oa = (unsigned long long)(k * ((2 * CHUNK_A) >> 4));
               const unsigned long long ow = (unsigned long long)(k * ((2 * CHUNK_W) >> 4));
               umma(d, ad_hi + oa, bd_hi + ow, k > 0 ? 1u : 0u);
@@ -315,10 +356,14 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       const uint4 z = make_uint4(0, 0, 0, 0);
       sts16(sm.a[0] + skc * CHUNK_A + srow * 16, valid ? h0 : z);
       if (SPLIT) sts16(sm.a[1] + skc * CHUNK_A + srow * 16, valid ? l0 : z);
-      if (job.input_kind == IN_OBS) {
+      if (job.input_kind == IN_OBS || job.input_kind == IN_FEAT) {
         if ((skc + 8) * 8 < ch.kin) {
           sts16(sm.a[0] + (skc + 8) * CHUNK_A + srow * 16, valid ? h1 : z);
           if (SPLIT) sts16(sm.a[1] + (skc + 8) * CHUNK_A + srow * 16, valid ? l1 : z);
+        }
+        if (KA > 128 && (skc + 16) * 8 < ch.kin) {
+          sts16(sm.a[0] + (skc + 16) * CHUNK_A + srow * 16, valid ? h2 : z);
+          if (SPLIT) sts16(sm.a[1] + (skc + 16) * CHUNK_A + srow * 16, valid ? l2 : z);
         }
       } else if (skc < ch.onehot_pad / 8) {              // one-hot action / code: a single fp16 1.0 in the hi part
         const int act = valid ? sact : -1;
@@ -362,8 +407,8 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             const int col = (c ? R0 + cb * 8 * G1 : cb * 8 * G0) + g * 8 + cq;
             const unsigned* rr = raw + 4 * ((c ? G0 : 0) + g);
             const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + col);
-            const float a0 = elu32<EXACT>(fmaf(__uint_as_float(rr[0]), isc, bi.x)), a1 = elu32<EXACT>(fmaf(__uint_as_float(rr[1]), isc, bi.y));
-            const float b0 = elu32<EXACT>(fmaf(__uint_as_float(rr[2]), isc, bi.x)), b1 = elu32<EXACT>(fmaf(__uint_as_float(rr[3]), isc, bi.y));
+            const float a0 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[0]), isc, bi.x)), a1 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[1]), isc, bi.y));
+            const float b0 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[2]), isc, bi.x)), b1 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[3]), isc, bi.y));
             unsigned hi, lo;
             if (SPLIT) {
               split2(a0, a1, hi, lo);
@@ -490,7 +535,7 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           epi_sync();
           if (soft_seg && (cb & 1) == 0 && (lane & 3) == 0) {
             const float4 oa = sm.part2[cb + 1][rA], ob = sm.part2[cb + 1][rB];
-            float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
+            float* dst = (kind == LK_PRED) ? value_dst : job.reward_dst;
             if (dst) {
               if (idxA >= 0) dst[idxA] = support_scalar(spa, SoftPart{oa.x, oa.y, oa.z});
               if (idxB >= 0) dst[idxB] = support_scalar(spb, SoftPart{ob.x, ob.y, ob.z});
@@ -528,15 +573,15 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             za += __shfl_xor_sync(0xffffffffu, za, off);
             zb += __shfl_xor_sync(0xffffffffu, zb, off);
           }
-          if (job.policy_dst) {
+          if (policy_dst) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 const int i = g * 8 + cq + j;
                 if (i < n) {
-                  if (idxA >= 0) job.policy_dst[(size_t)idxA * job.pstride + i] = __fdiv_rn(xa[2 * g + j], za);
-                  if (idxB >= 0) job.policy_dst[(size_t)idxB * job.pstride + i] = __fdiv_rn(xb[2 * g + j], zb);
+                  if (idxA >= 0) policy_dst[(size_t)idxA * job.pstride + i] = __fdiv_rn(xa[2 * g + j], za);
+                  if (idxB >= 0) policy_dst[(size_t)idxB * job.pstride + i] = __fdiv_rn(xb[2 * g + j], zb);
                 }
               }
           }
@@ -713,12 +758,12 @@ int smz_tc32_create(const SmzNetShape& sh, int nprod, SmzTc32Image** out, char* 
     n.scales = im->scales + i * 6;
   }
   im->bias_pool = (float*)p;
-  im->smem_bytes = (int)sizeof(SmemT) + 1024;
+  im->smem_bytes = (int)sizeof(SmemT<KMAX>) + 1024;
   im->nprod = nprod == 1 ? 1 : 3;
   im->exact_elu = (im->nprod == 3 && getenv("SMZ_TC32_POLY")) ? atoi(getenv("SMZ_TC32_POLY")) : 0;
-  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
-  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
-  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, false, false, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, true, false, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
+  cudaFuncSetAttribute((const void*)k_tc32_chain_m64<1, false, false, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
   *out = im;
   return SMZ_OK;
 }
@@ -837,7 +882,8 @@ void smz_tc32_read_hidden(const SmzArena& a, int slot, int n_trees, float* out, 
 static void launch(SmzTc32Image* im, dim3 grid, cudaStream_t s, bool pdl, const SmzArena& a, const Chain& c0, const Chain& c1,
                    Job job, int sim) {
   job.exact_elu = im->exact_elu;
-  auto* k = im->nprod == 1 ? k_tc32_chain_m64<1, false> : (im->exact_elu ? k_tc32_chain_m64<3, true> : k_tc32_chain_m64<3, false>);
+  auto* k = im->nprod == 1 ? k_tc32_chain_m64<1, false, false, KMAX>
+                           : (im->exact_elu ? k_tc32_chain_m64<3, true, false, KMAX> : k_tc32_chain_m64<3, false, false, KMAX>);
   smz_launch(k, grid, dim3(NTHR), (size_t)im->smem_bytes, s, pdl, a, c0, c1, job, sim);
 }
 
@@ -867,4 +913,132 @@ void smz_tc32_eval(SmzTc32Image* im, const SmzNetShape& sh, int which, int n_row
   job.code_dst = code_out; job.pstride = policy_stride;
   SmzArena dummy{};
   launch(im, dim3((n_rows + TM - 1) / TM), s, false, dummy, im->chain_single[which], im->chain_single[which], job, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// vision family: the MLP heads (147 -> H -> L x [H -> H] -> S or A, ReLU; neural_network_vision_model.py:188-199,
+// :262-296) of a simulation step on the same chain kernel, fp32-grade (three products), five (branch, head) chains
+// ---------------------------------------------------------------------------------------------
+struct SmzTc32VisionHeads {
+  int A, S, H, L;
+  unsigned char* pool;     // weight images + biases + chain biases
+  size_t pool_bytes;
+  __half* w[5][3];         // in (K = 160), mid, out images, each [hi | lo]
+  float* b[5][3];
+  float* bias_pool;        // [5][MAXL][128]
+  unsigned* absmax;        // device [15]
+  float* scales;           // device [15][2]
+  Chain* chains_dev;       // device [5]
+  int smem_bytes;
+};
+
+int smz_tc32_vision_create(int A, int S, int H, int L, SmzTc32VisionHeads** out, char* err, size_t err_len) {
+  if (L + 2 > MAXL || H > KMAX || S > 64 || A > 32) {
+    snprintf(err, err_len, "vision heads on tcgen05: need L <= %d, H <= %d, S <= 64, A <= 32", MAXL - 2, KMAX);
+    return SMZ_E_CAPACITY;
+  }
+  SmzTc32VisionHeads* im = new SmzTc32VisionHeads();
+  memset(im, 0, sizeof(*im));
+  im->A = A; im->S = S; im->H = H; im->L = L;
+  const size_t per_head = (size_t)(KVIS + 2 * KMAX) * TN * 2 * 2 + 3 * TN * 4;
+  im->pool_bytes = 5 * per_head + (size_t)5 * MAXL * TN * 4;
+  if (cudaMalloc(&im->pool, im->pool_bytes) != cudaSuccess || cudaMalloc(&im->absmax, 15 * sizeof(unsigned)) != cudaSuccess ||
+      cudaMalloc(&im->scales, 30 * sizeof(float)) != cudaSuccess || cudaMalloc(&im->chains_dev, 5 * sizeof(Chain)) != cudaSuccess) {
+    snprintf(err, err_len, "vision heads on tcgen05: cudaMalloc failed");
+    cudaFree(im->pool); cudaFree(im->absmax); cudaFree(im->scales); cudaFree(im->chains_dev);
+    delete im;
+    return SMZ_E_CUDA;
+  }
+  unsigned char* p = im->pool;
+  for (int h = 0; h < 5; ++h) {
+    const int K[3] = {KVIS, KMAX, KMAX};
+    for (int i = 0; i < 3; ++i) { im->w[h][i] = (__half*)p; p += (size_t)K[i] * TN * 2 * 2; }
+    for (int i = 0; i < 3; ++i) { im->b[h][i] = (float*)p; p += TN * 4; }
+  }
+  im->bias_pool = (float*)p;
+  im->smem_bytes = (int)sizeof(SmemT<KVIS>) + 1024;
+  if (cudaFuncSetAttribute((const void*)k_tc32_chain_m64<3, false, true, KVIS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           im->smem_bytes) != cudaSuccess) {
+    snprintf(err, err_len, "vision heads on tcgen05: %d bytes of shared memory per CTA are not available", im->smem_bytes);
+    smz_tc32_vision_destroy(im);
+    return SMZ_E_CAPACITY;
+  }
+  *out = im;
+  return SMZ_OK;
+}
+
+void smz_tc32_vision_destroy(SmzTc32VisionHeads* im) {
+  if (!im) return;
+  cudaFree(im->pool); cudaFree(im->absmax); cudaFree(im->scales); cudaFree(im->chains_dev);
+  delete im;
+}
+
+int smz_tc32_vision_pack(SmzTc32VisionHeads* im, const float* blob, const SmzVisionHeadSrc* src, cudaStream_t s, char* err,
+                         size_t err_len) {
+  if (cudaMemsetAsync(im->pool, 0, im->pool_bytes, s) != cudaSuccess || cudaMemsetAsync(im->absmax, 0, 15 * sizeof(unsigned), s) != cudaSuccess) {
+    snprintf(err, err_len, "vision heads on tcgen05: memset failed");
+    return SMZ_E_CUDA;
+  }
+  const int H = im->H, L = im->L, FLATK = 147;
+  for (int h = 0; h < 5; ++h) {
+    const SmzVisionHeadSrc& q = src[h];
+    k_absmax<<<64, 256, 0, s>>>(blob + q.in_w, H * FLATK, im->absmax + h * 3 + 0);
+    if (L > 0) k_absmax<<<64, 256, 0, s>>>(blob + q.mid_w, H * H, im->absmax + h * 3 + 1);
+    k_absmax<<<64, 256, 0, s>>>(blob + q.out_w, q.n_out * H, im->absmax + h * 3 + 2);
+  }
+  for (int i = 0; i < 15; ++i) k_scale_from_absmax<<<1, 1, 0, s>>>(im->absmax + i, im->scales + 2 * i, im->scales + 2 * i + 1);
+  for (int h = 0; h < 5; ++h) {
+    const SmzVisionHeadSrc& q = src[h];
+    const float* sc = im->scales + h * 6;
+    k_pack_split<<<(H * FLATK + 255) / 256, 256, 0, s>>>(im->w[h][0], KVIS, blob + q.in_w, sc + 0, H, FLATK, FLATK, 0, 0, 0, 0);
+    k_copy_f32<<<1, 128, 0, s>>>(im->b[h][0], blob + q.in_b, H);
+    if (L > 0) {
+      k_pack_split<<<(H * H + 255) / 256, 256, 0, s>>>(im->w[h][1], KMAX, blob + q.mid_w, sc + 2, H, H, H, 0, 0, 0, 0);
+      k_copy_f32<<<1, 128, 0, s>>>(im->b[h][1], blob + q.mid_b, H);
+    }
+    k_pack_split<<<(q.n_out * H + 255) / 256, 256, 0, s>>>(im->w[h][2], KMAX, blob + q.out_w, sc + 4, q.n_out, H, H, 0, 0, 0, 0);
+    k_fill_f32<<<1, 128, 0, s>>>(im->b[h][2], -1e30f, TN);          // padded logits: probability exactly 0
+    k_copy_f32<<<1, 128, 0, s>>>(im->b[h][2], blob + q.out_b, q.n_out);
+  }
+  float host_scales[30];
+  if (cudaMemcpyAsync(host_scales, im->scales, sizeof(host_scales), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    snprintf(err, err_len, "vision heads on tcgen05: reading the layer scales back failed");
+    return SMZ_E_CUDA;
+  }
+  Chain chains[5];
+  for (int h = 0; h < 5; ++h) {
+    Chain& ch = chains[h];
+    memset(&ch, 0, sizeof(ch));
+    float* bias_dst = im->bias_pool + (size_t)h * MAXL * TN;
+    int l = 0;
+    auto add = [&](int i, int K, int kind) {
+      ch.layer[l].w = im->w[h][i]; ch.layer[l].K = K; ch.layer[l].kind = kind;
+      ch.inv_scale[l] = host_scales[h * 6 + 2 * i + 1];
+      k_copy_f32<<<1, TN, 0, s>>>(bias_dst + (size_t)l * TN, im->b[h][i], TN);
+      ++l;
+    };
+    add(0, KVIS, LK_HIDDEN);
+    for (int i = 0; i < L; ++i) add(1, KMAX, LK_HIDDEN);
+    add(2, KMAX, src[h].is_policy ? LK_CODE : LK_PRED);
+    ch.n_layers = l; ch.bias = bias_dst; ch.kin = KVIS; ch.onehot_pad = 0;
+    ch.n_policy = src[h].is_policy ? src[h].n_out : 0;
+  }
+  if (cudaMemcpyAsync(im->chains_dev, chains, sizeof(chains), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    snprintf(err, err_len, "vision heads on tcgen05: weight packing failed");
+    return SMZ_E_CUDA;
+  }
+  return SMZ_OK;
+}
+
+// heads of simulation `sim` for the compacted rows of both branches; feat as written by the convolution stage
+void smz_tc32_vision_heads(SmzTc32VisionHeads* im, const SmzArena& a, int n_trees, int sim, const float* feat, cudaStream_t s) {
+  Job job{};
+  job.input_kind = IN_FEAT; job.n_rows = n_trees; job.S = im->S;
+  job.feat = feat; job.vchains = im->chains_dev;
+  job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
+  Chain none{};
+  smz_launch(k_tc32_chain_m64<3, false, true, KVIS>, dim3(5 * ((n_trees + TM - 1) / TM)), dim3(NTHR), (size_t)im->smem_bytes, s, false,
+             a, none, none, job, sim);
 }

@@ -18,3 +18,19 @@ void smz_tc32_eval(SmzTc32Image* im, const SmzNetShape& sh, int which, int n_row
                    int policy_stride, cudaStream_t s);
 // the arena keeps hidden states as [hi 64 | lo 64] fp16 rows in this mode; this widens one slot to fp32 rows
 void smz_tc32_read_hidden(const SmzArena& a, int slot, int n_trees, float* out, cudaStream_t s);
+
+// ---- vision family: the 147 -> H -> .. -> S / A MLP heads of a simulation step on the chain kernel (fp32-grade) ----
+struct SmzTc32VisionHeads;
+// where one head's Linear layers sit in the vision weight blob (offsets in floats)
+struct SmzVisionHeadSrc {
+  size_t in_w, in_b, mid_w, mid_b, out_w, out_b;
+  int n_out;       // S (categorical support) or A (policy)
+  int is_policy;
+};
+int smz_tc32_vision_create(int A, int S, int H, int L, SmzTc32VisionHeads** out, char* err, size_t err_len);
+void smz_tc32_vision_destroy(SmzTc32VisionHeads* im);
+// src[5]: afterstate value, afterstate policy, dynamics reward, dynamics value, dynamics policy
+int smz_tc32_vision_pack(SmzTc32VisionHeads* im, const float* blob_dev, const SmzVisionHeadSrc* src, cudaStream_t s, char* err,
+                         size_t err_len);
+// feat: [3 heads: reward, value, policy][2 branches][a.B rows][160] fp32, rows in the compacted order of the simulation
+void smz_tc32_vision_heads(SmzTc32VisionHeads* im, const SmzArena& a, int n_trees, int sim, const float* feat, cudaStream_t s);

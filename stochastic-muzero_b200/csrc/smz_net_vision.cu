@@ -13,10 +13,12 @@
 // The representation (98x98x3 -> 3x7x7) runs once per move, one CTA per tree, all feature maps in smem.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/smz.h"
 #include "smz_net_vision.h"
+#include "smz_net_tc32.h"
 
 namespace {
 
@@ -35,13 +37,17 @@ struct VPred { VRes res; const float *cv_w, *cv_b; VMlp value; const float *cp_w
 struct VRepr { const float* conv_in; VRes res_in; const float* conv_out; VRes res_out, res_last; };
 struct VNets { VRepr repr; VDyn dyn, adyn; VPred pred, apred; int A, S, H, L; };
 
+constexpr int RC = 8;               // leaves per CTA of the convolution-only stage (1024 trees = 128 CTAs on 148 SMs; measured on
+                                    // cfg5: 32 leaves 8.1, 8 leaves 13.9, 4 leaves 11.8 M sims/s)
+constexpr int NTC = 256;            // threads of that stage (512 measured slower: 11.7 M sims/s)
+template <int RT>                   // RT leaves per CTA
 struct SmemSim {
-  float x[R][LD];                 // MLP ping
-  float y[R][LD];                 // MLP pong
-  float w[2][KC][SMZ_HP];         // weight ring
-  float in4[R][4 * PIX];          // trunk input: state + action plane
-  float f0[R][FLAT], f1[R][FLAT], f2[R][FLAT];   // feature maps
-  int tree[R], slot[R], act[R];
+  float x[RT][LD];                // MLP ping / rows entering an MLP head
+  float y[RT == R ? R : 1][LD];   // MLP pong (CUDA-core heads only)
+  float w[2][RT == R ? KC : 1][SMZ_HP];   // weight ring (CUDA-core heads only)
+  float in4[RT][4 * PIX];         // trunk input: state + action plane
+  float f0[RT][FLAT], f1[RT][FLAT], f2[RT][FLAT];   // feature maps
+  int tree[RT], slot[RT], act[RT];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -292,17 +298,34 @@ struct VJob {
   float* hidden_dst;    // [index][160]
   float* policy_dst; float* value_dst; float* reward_dst;
   int pstride;
+  float* feat;          // FEAT stage: [3 heads][2 branches][B rows][160] inputs of the MLP heads (tensor-core stage)
 };
 
-__global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob job, int sim) {
+// MLP-head input rows of a tile -> the feature scratch the tensor-core stage reads
+template <int RT>
+__device__ void rows_to_feat(const float (*rows)[LD], float* feat, int head, int branch, int B, int tile, int n_valid) {
+  float* dst = feat + ((size_t)(head * 2 + branch) * B + (size_t)tile * RT) * VSP;
+  for (int e = threadIdx.x; e < RT * VSP; e += blockDim.x) {
+    const int r = e / VSP, c = e - r * VSP;
+    if (r < n_valid) dst[(size_t)r * VSP + c] = rows[r][c];
+  }
+  __syncthreads();
+}
+
+// FEAT = false: the whole step on the CUDA cores (three CTAs per tile, one per MLP head).  FEAT = true (simulation
+// step only): the convolution stage alone — trunk, new hidden state, residual trunk of the prediction net and the
+// three 1x1 convolutions; the rows that enter the MLP heads go to `job.feat`, the heads run on the tensor cores
+// (smz_tc32_vision_heads).
+template <bool FEAT, int R>
+__global__ void __launch_bounds__(FEAT ? NTC : NT) k_vision_step(SmzArena a, VNets nets, VJob job, int sim) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemSim& sm = *reinterpret_cast<SmemSim*>(smem_raw);
+  SmemSim<R>& sm = *reinterpret_cast<SmemSim<R>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Three CTAs share a tile of 32 leaves, one per MLP head (the heads are ~80 % of the work and independent):
   // head 0 = reward (dynamics pair only), 1 = value (also writes the new hidden state), 2 = policy.  The cheap
   // convolution trunk is recomputed by each.
-  const int head = blockIdx.x % 3;
-  int tile = blockIdx.x / 3, branch = 0, count = job.n_rows;
+  const int head = FEAT ? 1 : blockIdx.x % 3;
+  int tile = FEAT ? blockIdx.x : blockIdx.x / 3, branch = 0, count = job.n_rows;
   bool do_trunk = true, do_pred = true;
   if (job.mode == 0) {
     const int n0 = a.branch_count[sim * 2 + 0], n1 = a.branch_count[sim * 2 + 1];
@@ -319,8 +342,11 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
       branch = (job.which == 4 || job.which == 1) ? 1 : 0;
     }
   }
-  if (head == 0 && !(do_trunk && branch && (job.mode == 0 || job.which == 4))) return;   // no reward head here
-  if (head != 0 && !do_pred && !(head == 1 && do_trunk)) return;                            // nothing but a state write
+  if (!FEAT) {
+    if (head == 0 && !(do_trunk && branch && (job.mode == 0 || job.which == 4))) return;   // no reward head here
+    if (head != 0 && !do_pred && !(head == 1 && do_trunk)) return;                            // nothing but a state write
+  }
+  const int n_valid = min(R, count - tile * R);
   if (tid < R) {
     const int row = tile * R + tid;
     int tree = -1, slot = 0, act = 0;
@@ -332,7 +358,7 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
   }
   __syncthreads();
   // ---- load the input state of every row -----------------------------------------------------------------
-  for (int e = tid; e < R * 4 * PIX; e += NT) {
+  for (int e = tid; e < R * 4 * PIX; e += blockDim.x) {
     const int r = e / (4 * PIX), c = e - r * (4 * PIX);
     const int tree = sm.tree[r];
     float v = 0.f;
@@ -354,7 +380,7 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
     const VDyn& d = branch ? nets.dyn : nets.adyn;
     // conv(4->3) + BN + ReLU (folded: BN scale/shift applied to the conv OUTPUT, then ReLU)
     conv7<4, false>(&sm.in4[0][0], 4 * PIX, &sm.f0[0][0], FLAT, d.conv, nullptr, nullptr, nullptr, 0, R);
-    for (int e = tid; e < R * FLAT; e += NT) {
+    for (int e = tid; e < R * FLAT; e += blockDim.x) {
       const int c = (e % FLAT) / PIX;
       float* q = &sm.f0[0][0] + e;
       *q = fmaxf(fmaf(*q, __ldg(d.bn_s + c), __ldg(d.bn_t + c)), 0.f);
@@ -367,20 +393,27 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
     }
     scale_channels(x, FLAT, true, R);
     state = x;
-    for (int e = tid; e < R * VSP; e += NT) {
+    for (int e = tid; e < R * VSP; e += blockDim.x) {
       const int r = e / VSP, c = e - r * VSP;
       const int tree = sm.tree[r];
       if (head == 1 && tree >= 0 && job.hidden_dst) job.hidden_dst[(size_t)tree * VSP + c] = c < FLAT ? state[r * FLAT + c] : 0.f;
     }
-    if (head == 0 && branch && (job.mode == 0 || job.which == 4)) {
-      // reward head (vision:180, :207-215): conv1x1(4->3) on the INPUT x, flatten, MLP, categorical support
-      conv1x1_to_rows(&sm.in4[0][0], 4 * PIX, 4, d.cr_w, d.cr_b, sm.x, R);
-      float(*o)[LD] = mlp_head(d.reward, nets.L, sm.x, sm.y, sm.w);
-      for (int r = warp; r < R; r += NT / 32) {
-        const float rew = support_scalar(o[r], nets.S);
-        if (sm.tree[r] >= 0 && lane == 0 && job.reward_dst) job.reward_dst[sm.tree[r]] = rew;
+    if (FEAT) {
+      if (branch) {       // reward head input (vision:180, :207-215): conv1x1(4->3) on the INPUT x, flattened
+        conv1x1_to_rows(&sm.in4[0][0], 4 * PIX, 4, d.cr_w, d.cr_b, sm.x, R);
+        rows_to_feat<R>(sm.x, job.feat, 0, branch, a.B, tile, n_valid);
       }
-      __syncthreads();
+    } else if (head == 0 && branch && (job.mode == 0 || job.which == 4)) {
+      if constexpr (!FEAT) {
+        // reward head (vision:180, :207-215): conv1x1(4->3) on the INPUT x, flatten, MLP, categorical support
+        conv1x1_to_rows(&sm.in4[0][0], 4 * PIX, 4, d.cr_w, d.cr_b, sm.x, R);
+        float(*o)[LD] = mlp_head(d.reward, nets.L, sm.x, sm.y, sm.w);
+        for (int r = warp; r < R; r += NT / 32) {
+          const float rew = support_scalar(o[r], nets.S);
+          if (sm.tree[r] >= 0 && lane == 0 && job.reward_dst) job.reward_dst[sm.tree[r]] = rew;
+        }
+        __syncthreads();
+      }
     }
   }
   if (do_pred && head != 0) {
@@ -393,18 +426,25 @@ __global__ void __launch_bounds__(NT) k_vision_step(SmzArena a, VNets nets, VJob
       resblock7(p.res, x, t1, t2, R);
       float* t = x; x = t1; t1 = t;
     }
-    if (head == 1) {
+    if (FEAT) {
       conv1x1_to_rows(x, FLAT, 3, p.cv_w, p.cv_b, sm.x, R);
-      float(*ov)[LD] = mlp_head(p.value, nets.L, sm.x, sm.y, sm.w);
-      for (int r = warp; r < R; r += NT / 32) {
-        const float val = support_scalar(ov[r], nets.S);
-        if (sm.tree[r] >= 0 && lane == 0 && job.value_dst) job.value_dst[sm.tree[r]] = val;
-      }
-    } else {
+      rows_to_feat<R>(sm.x, job.feat, 1, branch, a.B, tile, n_valid);
       conv1x1_to_rows(x, FLAT, 3, p.cp_w, p.cp_b, sm.x, R);
-      float(*op)[LD] = mlp_head(p.policy, nets.L, sm.x, sm.y, sm.w);
-      for (int r = warp; r < R; r += NT / 32)
-        if (sm.tree[r] >= 0 && job.policy_dst) policy_softmax(op[r], nets.A, job.policy_dst + (size_t)sm.tree[r] * job.pstride);
+      rows_to_feat<R>(sm.x, job.feat, 2, branch, a.B, tile, n_valid);
+    } else if constexpr (!FEAT) {
+      if (head == 1) {
+        conv1x1_to_rows(x, FLAT, 3, p.cv_w, p.cv_b, sm.x, R);
+        float(*ov)[LD] = mlp_head(p.value, nets.L, sm.x, sm.y, sm.w);
+        for (int r = warp; r < R; r += NT / 32) {
+          const float val = support_scalar(ov[r], nets.S);
+          if (sm.tree[r] >= 0 && lane == 0 && job.value_dst) job.value_dst[sm.tree[r]] = val;
+        }
+      } else {
+        conv1x1_to_rows(x, FLAT, 3, p.cp_w, p.cp_b, sm.x, R);
+        float(*op)[LD] = mlp_head(p.policy, nets.L, sm.x, sm.y, sm.w);
+        for (int r = warp; r < R; r += NT / 32)
+          if (sm.tree[r] >= 0 && job.policy_dst) policy_softmax(op[r], nets.A, job.policy_dst + (size_t)sm.tree[r] * job.pstride);
+      }
     }
   }
 }
@@ -503,6 +543,11 @@ struct SmzVisionImage {
   float* pool;
   size_t pool_floats;
   uint64_t blob_floats;
+  // tensor-core stage of the simulation step (null: SMZ_VISION_CC=1 or not available -> CUDA-core heads)
+  SmzTc32VisionHeads* tc;
+  SmzVisionHeadSrc head_src[5];     // afterstate value / policy, dynamics reward / value / policy
+  float* feat;                      // [3][2][max_trees][160]
+  int max_trees;
 };
 
 namespace {
@@ -534,13 +579,18 @@ struct Builder {
     boff += n;
     return d;
   }
+  SmzVisionHeadSrc last_src{};      // blob offsets of the head packed last (for the tensor-core image)
   VMlp mlp(int n_out) {
     VMlp m{};
-    m.in_wt = wt(H, FLAT, VSP); m.in_b = vec128(H);
-    if (L > 0) { m.mid_wt = wt(H, H, SMZ_HP); m.mid_b = vec128(H); }
-    m.out_wt = wt(n_out, H, SMZ_HP); m.out_b = vec128(n_out);
+    SmzVisionHeadSrc q{};
+    q.n_out = n_out;
+    q.in_w = boff; m.in_wt = wt(H, FLAT, VSP); q.in_b = boff; m.in_b = vec128(H);
+    if (L > 0) { q.mid_w = boff; m.mid_wt = wt(H, H, SMZ_HP); q.mid_b = boff; m.mid_b = vec128(H); }
+    q.out_w = boff; m.out_wt = wt(n_out, H, SMZ_HP); q.out_b = boff; m.out_b = vec128(n_out);
+    last_src = q;
     return m;
   }
+  SmzVisionHeadSrc src[5];
   VNets all() {
     VNets n{};
     n.A = A; n.S = S; n.H = H; n.L = L;
@@ -548,13 +598,13 @@ struct Builder {
     for (int i = 0; i < 2; ++i) {
       VDyn& d = i ? n.adyn : n.dyn;
       d.conv = raw(108); bn(3, &d.bn_s, &d.bn_t); d.res = res(3);
-      if (i == 0) { d.cr_w = raw(12); d.cr_b = raw(3); d.reward = mlp(S); }
+      if (i == 0) { d.cr_w = raw(12); d.cr_b = raw(3); d.reward = mlp(S); src[2] = last_src; }
     }
     for (int i = 0; i < 2; ++i) {
       VPred& p = i ? n.apred : n.pred;
       p.res = res(3);
-      p.cv_w = raw(9); p.cv_b = raw(3); p.value = mlp(S);
-      p.cp_w = raw(9); p.cp_b = raw(3); p.policy = mlp(A);
+      p.cv_w = raw(9); p.cv_b = raw(3); p.value = mlp(S); src[i ? 0 : 3] = last_src;
+      p.cp_w = raw(9); p.cp_b = raw(3); p.policy = mlp(A); src[i ? 1 : 4] = last_src; src[i ? 1 : 4].is_policy = 1;
     }
     return n;
   }
@@ -567,7 +617,7 @@ uint64_t smz_vision_blob_floats(int A, int S, int H, int L) {
   return b.boff;
 }
 
-int smz_vision_create(int A, int S, int H, int L, SmzVisionImage** out, char* err, size_t err_len) {
+int smz_vision_create(int A, int S, int H, int L, int max_trees, SmzVisionImage** out, char* err, size_t err_len) {
   if (H > SMZ_HP || S > SMZ_SP || A > 32 || L < 1 || L > 16) {
     snprintf(err, err_len, "vision network: need H<=%d, S<=%d, A<=32, 1<=L<=16 (got %d, %d, %d, %d)", SMZ_HP, SMZ_SP, H, S, A, L);
     return SMZ_E_CAPACITY;
@@ -578,13 +628,26 @@ int smz_vision_create(int A, int S, int H, int L, SmzVisionImage** out, char* er
   b.all();
   im->pool_floats = b.poff;
   im->blob_floats = b.boff;
+  memcpy(im->head_src, b.src, sizeof(im->head_src));
+  im->max_trees = max_trees;
   if (cudaMalloc(&im->pool, im->pool_floats * sizeof(float)) != cudaSuccess) {
     snprintf(err, err_len, "vision network: cudaMalloc of the weight image failed");
     delete im;
     return SMZ_E_CUDA;
   }
   im->nets.A = A; im->nets.S = S; im->nets.H = H; im->nets.L = L;
-  cudaFuncSetAttribute((const void*)k_vision_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSim));
+  // the MLP heads of the simulation step on the tensor cores (fp32-grade chain) unless SMZ_VISION_CC=1 asks for the
+  // all-CUDA-core kernel; stand-alone evaluation and the root prediction always use the latter
+  if (!getenv("SMZ_VISION_CC")) {
+    char why[256] = "";
+    if (smz_tc32_vision_create(A, S, H, L, &im->tc, why, sizeof(why)) != SMZ_OK) im->tc = nullptr;
+    if (im->tc && cudaMalloc(&im->feat, (size_t)6 * max_trees * VSP * sizeof(float)) != cudaSuccess) {
+      smz_tc32_vision_destroy(im->tc);
+      im->tc = nullptr;
+    }
+  }
+  cudaFuncSetAttribute((const void*)k_vision_step<false, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSim<R>));
+  cudaFuncSetAttribute((const void*)k_vision_step<true, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSim<RC>));
   cudaFuncSetAttribute((const void*)k_vision_repr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRepr));
   *out = im;
   return SMZ_OK;
@@ -592,6 +655,8 @@ int smz_vision_create(int A, int S, int H, int L, SmzVisionImage** out, char* er
 
 void smz_vision_destroy(SmzVisionImage* im) {
   if (!im) return;
+  if (im->tc) smz_tc32_vision_destroy(im->tc);
+  cudaFree(im->feat);
   cudaFree(im->pool);
   delete im;
 }
@@ -603,6 +668,10 @@ int smz_vision_pack(SmzVisionImage* im, const float* blob_dev, cudaStream_t s, c
   }
   Builder b{blob_dev, im->pool, 0, 0, s, false, im->nets.A, im->nets.S, im->nets.H, im->nets.L};
   im->nets = b.all();
+  if (im->tc) {
+    const int rc = smz_tc32_vision_pack(im->tc, blob_dev, im->head_src, s, err, err_len);
+    if (rc != SMZ_OK) return rc;
+  }
   if (cudaGetLastError() != cudaSuccess) {
     snprintf(err, err_len, "vision network: weight packing launch failed");
     return SMZ_E_CUDA;
@@ -614,15 +683,23 @@ void smz_vision_root(SmzVisionImage* im, const SmzArena& a, int n_trees, const f
   k_vision_repr<<<n_trees, NT, sizeof(SmemRepr), s>>>(im->nets, n_trees, obs, a.hidden);
   VJob job{};
   job.mode = 1; job.n_rows = n_trees; job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.pstride = a.W;
-  k_vision_step<<<3 * ((n_trees + R - 1) / R), NT, sizeof(SmemSim), s>>>(a, im->nets, job, 0);
+  k_vision_step<false, R><<<3 * ((n_trees + R - 1) / R), NT, sizeof(SmemSim<R>), s>>>(a, im->nets, job, 0);
 }
 
-void smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, cudaStream_t s) {
+// returns the number of kernels launched
+int smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, cudaStream_t s) {
   VJob job{};
   job.mode = 0; job.n_rows = n_trees;
   job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * VSP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
-  k_vision_step<<<3 * ((n_trees + R - 1) / R + 1), NT, sizeof(SmemSim), s>>>(a, im->nets, job, sim);
+  if (im->tc && n_trees <= im->max_trees) {
+    job.feat = im->feat;
+    k_vision_step<true, RC><<<(n_trees + RC - 1) / RC + 1, NTC, sizeof(SmemSim<RC>), s>>>(a, im->nets, job, sim);
+    smz_tc32_vision_heads(im->tc, a, n_trees, sim, im->feat, s);
+    return 2;
+  }
+  k_vision_step<false, R><<<3 * ((n_trees + R - 1) / R + 1), NT, sizeof(SmemSim<R>), s>>>(a, im->nets, job, sim);
+  return 1;
 }
 
 int smz_vision_eval(SmzVisionImage* im, int which, int n_rows, const float* in, const int* idx, float* hidden_out,
@@ -637,6 +714,6 @@ int smz_vision_eval(SmzVisionImage* im, int which, int n_rows, const float* in, 
   job.hidden_dst = hidden_out; job.policy_dst = policy_out; job.value_dst = value_out; job.reward_dst = reward_out;
   job.pstride = policy_stride;
   SmzArena dummy{};
-  k_vision_step<<<3 * ((n_rows + R - 1) / R), NT, sizeof(SmemSim), s>>>(dummy, im->nets, job, 0);
+  k_vision_step<false, R><<<3 * ((n_rows + R - 1) / R), NT, sizeof(SmemSim<R>), s>>>(dummy, im->nets, job, 0);
   return SMZ_OK;
 }

@@ -1109,3 +1109,56 @@ def test_bf16_search_result_fidelity_against_reference_precision(name):
     ident, action, p99 = agreement("fp32", "tc32")
     assert ident >= 0.995 and action >= 0.999 and p99 <= 1e-4, \
         f"{name}: tc32 vs fp32 identical {ident:.4f}, same action {action:.4f}, root value p99 {p99:.2e}"
+
+
+# inverse_transform_with_support in fp32 (muzero_model.py:575-591): sqrt(1 + 0.004 (|y| + 1.001)) - 1 keeps ~14 bits,
+# so the scalar moves in steps ("quanta") of ~1.2e-4 near zero — one ulp of the categorical expectation y can move the
+# reference's own fp32 output by one quantum (tests/test_host_logic.py shows it against float64)
+SCALAR_QUANTUM_TOL = dict(atol=2.5e-4, rtol=1e-4)
+
+
+def test_vision_tensor_core_heads_match_the_cuda_core_step(monkeypatch):
+    """Simulation step of the vision family: convolution stage on the CUDA cores + MLP heads on the fp32-grade tcgen05
+    chain (default) against the all-CUDA-core kernel (SMZ_VISION_CC=1), driven step by step.  Wherever both engines
+    feed the network the same input (same parent hidden state — itself produced from equal inputs — and same action),
+    the outputs must agree: policies within 1e-5, scalars within one quantum of the support transform, the new
+    hidden state bit for bit (same convolution code).  Ragged batch: 300 trees = partial 8-, 32- and 64-row tiles."""
+    z = golden_io.load_vision_case("a4")
+    A = int(z["dims"][0])
+    B, N, seed = 300, 24, 5
+    obs = torch.rand(B, 3, 98, 98, generator=torch.Generator().manual_seed(8)).reshape(B, -1)
+    out = {}
+    for mode in ("tc", "cc"):
+        monkeypatch.delenv("SMZ_VISION_CC", raising=False)
+        if mode == "cc":
+            monkeypatch.setenv("SMZ_VISION_CC", "1")
+        eng = _vision_engine(z, B=B, N=N, rng="philox", seed=seed, record=True)
+        eng.root(obs=obs, train=True)
+        sel = []
+        for s in range(N):
+            sel.append([t.cpu().numpy() for t in eng.select(s)])
+            eng.net_step(s)
+            eng.expand_backup(s)
+        st = eng.stats()
+        assert st["launches"] == 4 + (3 if mode == "tc" else 2) * N + N, st       # the tensor-core stage is a kernel of its own
+        rec = {k: v.cpu().numpy() for k, v in eng.read_record().items()}
+        hid = np.stack([eng.read_hidden(k).cpu().numpy() for k in range(N + 1)], 1)          # [B, N+1, 147]
+        out[mode] = (np.array(sel), rec, hid)
+        eng.close()
+    (sa, ra, ha), (sb, rb, hb) = out["tc"], out["cc"]
+    rows = np.arange(B)
+    clean = np.zeros((B, N + 1), bool)            # hidden slot k holds a state both engines derived from equal inputs
+    clean[:, 0] = True
+    compared = 0
+    for s in range(N):
+        eq = (sa[s] == sb[s]).all(0) & clean[rows, sa[s][0]]
+        clean[:, s + 1] = eq
+        compared += int(eq.sum())
+        np.testing.assert_array_equal(ha[eq, s + 1], hb[eq, s + 1])
+        np.testing.assert_allclose(ra["sim_policy"][eq, s, :A], rb["sim_policy"][eq, s, :A], atol=1e-5)
+        np.testing.assert_allclose(ra["sim_value"][eq, s], rb["sim_value"][eq, s], **SCALAR_QUANTUM_TOL)
+        np.testing.assert_allclose(ra["sim_reward"][eq, s], rb["sim_reward"][eq, s], **SCALAR_QUANTUM_TOL)
+    assert compared >= 0.9 * B * N, f"only {compared} of {B * N} network evaluations had equal inputs"
+    both = clean[:, 1:]
+    exact = (ra["sim_value"][both] == rb["sim_value"][both]).mean()
+    assert exact >= 0.9, f"only {exact:.3f} of the compared values are bit-identical"

@@ -236,3 +236,29 @@ def test_search_object_can_be_copied_and_pickled():
         assert clone.cycle.global_step() == 0
     m._engines.clear()
     assert Monte_carlo_tree_search(num_simulations=3, max_batch=32)._offset(8) == 0     # no process group: rank 0
+
+
+def test_support_transform_fp32_is_quantised_near_zero():
+    """Why value / reward scalars are compared with a looser bar than 1e-5: the reference evaluates
+    inverse_transform_with_support (muzero_model.py:575-591) in float32, where sqrt(1 + 0.004 (|y| + 1.001)) - 1 cancels
+    ~2.5 decimal digits.  Against float64 the reference's OWN formula is off by up to ~1e-4 near zero, and its output
+    moves in whole quanta of ~1.2e-4."""
+    f32 = np.float32
+
+    def transform32(y):
+        y = f32(y)
+        inner = np.sqrt(f32(1) + f32(4) * f32(0.001) * (np.abs(y) + f32(1) + f32(0.001)), dtype=np.float32)
+        return np.sign(y) * (((inner - f32(1)) / (f32(2) * f32(0.001))) ** 2 - f32(1))
+
+    def transform64(y):
+        y = np.float64(y)
+        return np.sign(y) * (((np.sqrt(1 + 4 * 0.001 * (abs(y) + 1 + 0.001)) - 1) / (2 * 0.001)) ** 2 - 1)
+    ys = np.random.default_rng(0).uniform(0.01, 0.5, 4000).astype(np.float32)
+    err = np.array([abs(float(transform32(y)) - transform64(y)) for y in ys])
+    assert 5e-5 < err.max() < 2.5e-4                       # the fp32 formula itself is ~1e-4 away from the exact value
+    # as a function of y the fp32 output is a staircase: over a y interval of 1e-3 it takes a few dozen values only,
+    # a whole quantum (~1.2e-4) apart — two evaluations whose y differ in the last bits agree exactly or by one quantum
+    sweep = np.linspace(0.1, 0.101, 4001).astype(np.float32)
+    vals = np.unique(np.array([float(transform32(y)) for y in sweep]))
+    jumps = np.diff(vals)
+    assert len(vals) < 40 and 5e-5 < jumps.min() and jumps.max() < 2.5e-4
