@@ -178,15 +178,18 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   e->cfg.lanes_per_tree = lanes;
 
   const size_t B = a.B, M = a.M;
+  a.row_cap = (a.B + 127) / 128 * 128 + 128;
+  a.row_top = a.row_cap;
+  const size_t RC = a.row_cap;
   cudaError_t r = cudaSuccess;
 #define ALLOC(ptr, n) if (r == cudaSuccess) r = dev_alloc(e, &(ptr), (n))
   ALLOC(a.stat, B * M); ALLOC(a.link, B * M); ALLOC(a.root_prior, B * a.A); ALLOC(a.minmax, B);
   ALLOC(a.ucursor, B); ALLOC(a.root_to_play, B); ALLOC(a.path, B * a.path_stride); ALLOC(a.path_len, B);
   ALLOC(a.leaf_node, B); ALLOC(a.leaf_slot, B); ALLOC(a.leaf_action, B); ALLOC(a.leaf_branch, B);
-  ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 4 * B); ALLOC(a.rows4, 4 * B); ALLOC(a.error_flag, 1);
+  ALLOC(a.branch_count, (size_t)(a.N + 1) * 2); ALLOC(a.rows, 2 * RC); ALLOC(a.rows4, 2 * RC); ALLOC(a.error_flag, 1);
   ALLOC(a.depth_sum, 1);
   a.xin_q = c.net_mode == SMZ_NET_TC32 ? 16 : 8;
-  if (c.net_mode == SMZ_NET_BF16 || c.net_mode == SMZ_NET_TC32 || c.net_mode == SMZ_NET_F16) { ALLOC(a.xin, 4 * B * a.xin_q); }
+  if (c.net_mode == SMZ_NET_BF16 || c.net_mode == SMZ_NET_TC32 || c.net_mode == SMZ_NET_F16) { ALLOC(a.xin, 2 * RC * a.xin_q); }
   if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8); }
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
@@ -228,9 +231,9 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
     if (cudaMemcpy(e->seed_dev, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SMZ_E_CUDA, "seed upload failed");
   }
   if (rc == SMZ_OK && a.hidden) {
-    cudaMemset(a.rows, 0, 4 * B * sizeof(int));          // speculative gathers read rows beyond the live count
-    cudaMemset(a.rows4, 0, 4 * B * sizeof(int4));
-    if (a.xin) cudaMemset(a.xin, 0, 4 * B * a.xin_q * sizeof(uint4));
+    cudaMemset(a.rows, 0, 2 * RC * sizeof(int));          // speculative gathers read rows beyond the live count
+    cudaMemset(a.rows4, 0, 2 * RC * sizeof(int4));
+    if (a.xin) cudaMemset(a.xin, 0, 2 * RC * a.xin_q * sizeof(uint4));
     cudaError_t m = cudaMemset(a.hidden, 0, (size_t)(a.N + 1) * B * a.Sp * sizeof(float));
     if (m != cudaSuccess) rc = fail(SMZ_E_CUDA, "memset: %s", cudaGetErrorString(m));
   }
@@ -388,6 +391,7 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   count_launches(e, 1);
   CU(cudaGetLastError());
   e->n_trees = n_trees;
+  a.row_top = (n_trees + 127) / 128 * 128 + 128;    // see smz_common.cuh: rows of the two branches never share a tile
   e->sims_done = 0;
   return SMZ_OK;
 }

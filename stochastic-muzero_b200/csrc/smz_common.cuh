@@ -22,6 +22,7 @@
 struct SmzArena {
   // shape
   int B, N, A, C, K, Kd, Kc, Kmax, M, W, Sp, path_stride, n_phases;
+  int row_cap, row_top;   // compacted-row arrays: row_cap positions per parity; the current search uses [0, row_top)
   // tree columns
   int4* stat;
   int2* link;
@@ -38,8 +39,11 @@ struct SmzArena {
   int* leaf_branch; // [B]
   int* branch_count; // [N+1][2] rows per branch of each simulation
   // compacted rows of a simulation, double-buffered by simulation parity (the descent of sim s+1 may run in
-  // the tail of the kernel that still gathers sim s in another CTA): index smz_row_index(a, sim, branch, row)
-  int* rows;        // [2 parities][2 branches][B] tree ids
+  // the tail of the kernel that still gathers sim s in another CTA): index smz_row_index(a, sim, branch, row).
+  // ONE array of row_top positions per parity: afterstate rows grow upward from 0, dynamics rows downward from
+  // row_top - 1.  row_top = (ceil(trees / 128) + 1) * 128, so a tile of 32 / 64 / 128 consecutive positions never
+  // holds rows of both branches and a network CTA can request its positions before the branch counts are known.
+  int* rows;        // [2 parities][row_cap] tree ids
   int4* rows4;      // same order: {tree, parent hidden slot, action, 0} — one load per gathered row
   uint4* xin;       // same order, tensor-core networks only (else null): the parent's hidden row (xin_q x 16 B), copied by
                     // the descent so that the network step gathers with ONE dependent load instead of two
@@ -77,7 +81,7 @@ struct SmzArena {
 
 #ifdef __CUDACC__
 __device__ __forceinline__ size_t smz_row_index(const SmzArena& a, int sim, int branch, int row) {
-  return (size_t)((sim & 1) * 2 + branch) * a.B + row;
+  return (size_t)(sim & 1) * a.row_cap + (branch ? a.row_top - 1 - row : row);
 }
 // Programmatic dependent launch (PDL): `smz_pdl_wait` blocks until the preceding kernel of the stream has
 // completed and its writes are visible (no-op when the launch carries no programmatic dependency);

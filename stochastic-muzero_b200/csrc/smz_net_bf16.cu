@@ -734,7 +734,7 @@ constexpr unsigned IDESC64 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TN
 struct Smem64 {
   alignas(1024) unsigned char a[A64_BYTES];
   alignas(1024) unsigned char w[2][W_BYTES];
-  float bias[MAXL][TN];
+  float bias[2][MAXL][TN];   // both chains: the branch of a tile is known only after the dependency wait
   unsigned long long wbar[2];
   unsigned long long dbar[2];
   unsigned long long bbar;
@@ -755,32 +755,37 @@ __device__ __forceinline__ void a64_store2(unsigned char* a, int row, int col, u
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(s32(a + (col >> 3) * CHUNK_A64 + row * 16 + (col & 7) * 2)), "r"(v) : "memory");
 }
 
-// R0 = columns of the first hidden-layer round (64: two even rounds; 96: 96 + 32, two K-steps left for the tail)
-template <int R0>
-__global__ void __launch_bounds__(NPIPE, 1)
+// R0 = columns of the first hidden-layer round (64: two even rounds; 96: 96 + 32, two K-steps left for the tail).
+// HALF = 32 leaves per tile instead of 64: the leaves sit in the accumulator rows m with m % 16 < 8, i.e. in the FIRST
+// row of every thread's 16x256b fragment (thread t: rows t/4 and t/4 + 8), so the epilogue — bound by the MUFU pipe and
+// by instruction issue, not by the contraction — does half the work per SM with all 32 lanes of every warp busy, on
+// twice as many SMs.  Chosen while the tiles of the batch fit one wave of SMs.
+// Tile -> rows: CTA i owns positions [i * TV, (i + 1) * TV) of the simulation's row array (smz_common.cuh: afterstate rows
+// from the bottom, dynamics rows from the top, never both in one tile), so the row records are requested together with
+// the branch counts — one L2 round trip after the dependency wait — and no CTA is launched for an empty tile of
+// the "other" branch.  The first weight tile of BOTH chains is prefetched before the wait.
+template <int R0, bool HALF>
+__global__ void __maxnreg__(80)
 k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
   Smem64& sm = *reinterpret_cast<Smem64*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int TV = HALF ? 32 : 64;       // leaves per tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer_warp = warp == NEPI / 32;
   const int q = warp & 3;                  // TMEM lane quarter: tile rows 16q .. 16q+15
   const int cb = (warp >> 2) & 3;          // head layers: 32-column block; hidden layers: 16-column slice of a round
-  const int rA = 16 * q + (lane >> 2), rB = rA + 8;     // the two tile rows of this thread's fragment
+  const int rA = 16 * q + (lane >> 2), rB = rA + 8;     // the two tile rows of this thread's fragment (HALF: rB is empty)
   const int cq = 2 * (lane & 3);           // column offset inside an 8-column group
 
-  int tile = blockIdx.x;
-  const int T = (job.n_rows + TM64 - 1) / TM64;
-  const int branch = tile >= T;
-  tile -= branch * T;
-  const Chain& ch = branch ? chain1 : chain0;
-  const int nl = ch.n_layers;
+  const int tile = blockIdx.x;
+  const int nl = chain0.n_layers;          // == chain1.n_layers (both pairs are 2 (L + 2) layers)
   long long* tl = (job.timeline && blockIdx.x == 0 && lane == 0) ? job.timeline : nullptr;   // debug stamps
   if (tl && tid == 0) tl[0] = clock64();
 
-  auto load_weights = [&](int l) {
-    const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
-    mbar_expect_tx(&sm.wbar[l & 1], bytes);
-    bulk_g2s(sm.w[l & 1], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
+  auto load_weights = [&](const Chain& c, int l, int slot) {
+    const unsigned bytes = (unsigned)c.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[slot], bytes);
+    bulk_g2s(sm.w[slot], c.layer[l].w, bytes, &sm.wbar[slot]);
   };
   if (tid == 0) {
     mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
@@ -788,10 +793,11 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     mbar_init(&sm.bbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const unsigned bbytes = (unsigned)nl * TN * 4;
-    mbar_expect_tx(&sm.bbar, bbytes);
-    bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
-    load_weights(0);
-    if (nl > 1) load_weights(1);
+    mbar_expect_tx(&sm.bbar, 2 * bbytes);
+    bulk_g2s(sm.bias[0], chain0.bias, bbytes, &sm.bbar);
+    bulk_g2s(sm.bias[1], chain1.bias, bbytes, &sm.bbar);
+    load_weights(chain0, 0, 0);
+    load_weights(chain1, 0, 1);
   }
   __syncwarp();
   if (warp == 0) {
@@ -802,12 +808,15 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   smz_pdl_wait();
   smz_pdl_launch_dependents();
   if (tl && tid == 0) tl[1 + 4 * MAXL] = clock64();
-  // gather: epilogue thread i stages the 16-byte K-chunk (i >> 6) of tile row (i & 63); requested before the count
-  const int srow = tid & 63, skc = (tid >> 6) & 7;
+  // gather: a staging thread owns the 16-byte K-chunk skc of leaf srow of the tile; requested before the counts are known
+  const bool stager = HALF ? tid < 256 : !is_issuer_warp;
+  const int srow = HALF ? (tid & 31) : (tid & 63), skc = HALF ? ((tid >> 5) & 7) : ((tid >> 6) & 7);
+  const int mrow = HALF ? 16 * (srow >> 3) + (srow & 7) : srow;     // accumulator row of that leaf
+  const int pos = tile * TV + srow;
   int4 rec = make_int4(0, 0, 0, 0);
   uint4 hrow = make_uint4(0, 0, 0, 0);
-  if (!is_issuer_warp) {
-    const size_t ri = smz_row_index(a, sim, branch, min(tile * TM64 + srow, a.B - 1));
+  if (stager) {
+    const size_t ri = (size_t)(sim & 1) * a.row_cap + pos;
     rec = a.rows4[ri];
     if (a.xin) {
       hrow = a.xin[ri * 8 + skc];              // the descent copied the parent's row: no dependent second load
@@ -818,12 +827,14 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
                                              ((size_t)rec.y * a.B + rec.x) * SMZ_SP + skc * 8);
     }
   }
-  const int count = a.branch_count[sim * 2 + branch];
-  if (tile * TM64 >= count) {
+  const int count0 = a.branch_count[sim * 2], count1 = a.branch_count[sim * 2 + 1];
+  const int top1 = a.row_top - count1;      // dynamics rows occupy [top1, row_top)
+  const int branch = tile * TV < count0 ? 0 : ((tile + 1) * TV > top1 ? 1 : -1);
+  if (branch < 0) {
     if (tid == 0) {
       mbar_wait(&sm.bbar, 0);
       mbar_wait(&sm.wbar[0], 0);
-      if (nl > 1) mbar_wait(&sm.wbar[1], 0);
+      mbar_wait(&sm.wbar[1], 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -832,6 +843,9 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(2 * TN) : "memory");
     return;
   }
+  const Chain& ch = branch ? chain1 : chain0;
+  // weight ring: layer l lives in slot (l + branch) & 1 (layer 0 of chain b was prefetched into slot b); the other
+  // slot's first fill was the unused chain's tile, so the fill that carries layer l is number (l + 1) >> 1 of its slot
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -839,10 +853,16 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 
   if (is_issuer_warp) {
     const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A64, 128);
+    if (nl > 1) {                              // layer 1 replaces the unused chain's prefetched tile
+      mbar_wait(&sm.wbar[(1 + branch) & 1], 0);
+      if (lane == 0) load_weights(ch, 1, (1 + branch) & 1);
+      __syncwarp();
+    }
     for (int l = 0; l < nl; ++l) {
       const int nk = ch.layer[l].K / 16;
-      mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
-      const unsigned long long bd = umma_desc(s32(sm.w[l & 1]), CHUNK_W, 128);
+      const int slot = (l + branch) & 1;
+      mbar_wait(&sm.wbar[slot], ((l + 1) >> 1) & 1);
+      const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
       for (int c = 0; c < 2; ++c) {
         nb_sync(2 + c);
@@ -862,28 +882,39 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       __syncwarp();
       if (l + 2 < nl) {
         mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
-        if (lane == 0) load_weights(l + 2);
+        if (lane == 0) load_weights(ch, l + 2, slot);
         __syncwarp();
       }
     }
   } else {
     {   // stage the first A operand
-      const bool valid = tile * TM64 + srow < count;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(sm.a + skc * CHUNK_A64 + srow * 16)), "r"(valid ? hrow.x : 0u),
-                   "r"(valid ? hrow.y : 0u), "r"(valid ? hrow.z : 0u), "r"(valid ? hrow.w : 0u)
-                   : "memory");
-      if (skc < ch.onehot_pad / 8) {
-        const int act = valid ? rec.z : -1;
-        unsigned w4[4] = {0, 0, 0, 0};
-        if (act >= skc * 8 && act < skc * 8 + 8) {
-          const int j = act - skc * 8;
-          w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(sm.a + (8 + skc) * CHUNK_A64 + srow * 16)), "r"(w4[0]),
-                     "r"(w4[1]), "r"(w4[2]), "r"(w4[3])
+      if (stager) {
+        const bool valid = branch ? pos >= top1 : pos < count0;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(sm.a + skc * CHUNK_A64 + mrow * 16)), "r"(valid ? hrow.x : 0u),
+                     "r"(valid ? hrow.y : 0u), "r"(valid ? hrow.z : 0u), "r"(valid ? hrow.w : 0u)
                      : "memory");
+        if (skc < ch.onehot_pad / 8) {
+          const int act = valid ? rec.z : -1;
+          unsigned w4[4] = {0, 0, 0, 0};
+          if (act >= skc * 8 && act < skc * 8 + 8) {
+            const int j = act - skc * 8;
+            w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(sm.a + (8 + skc) * CHUNK_A64 + mrow * 16)), "r"(w4[0]),
+                       "r"(w4[1]), "r"(w4[2]), "r"(w4[3])
+                       : "memory");
+        }
+        if (skc == 0) sm.rowidx[mrow] = valid ? rec.x : -1;
+      } else {
+        // HALF: the accumulator rows m % 16 >= 8 carry no leaf — zero operand rows (nothing ever reads their results)
+        const int j = tid - 256;
+        const int zrow = 16 * ((j >> 3) & 3) + 8 + (j & 7), zc = j >> 5;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(s32(sm.a + (zc + 8 * h) * CHUNK_A64 + zrow * 16)), "r"(0u)
+                       : "memory");
+        if (zc == 0) sm.rowidx[zrow] = -1;
       }
-      if (skc == 0) sm.rowidx[srow] = valid ? rec.x : -1;
     }
     fence_async_smem();
     for (int c = 0; c < 2; ++c) nb_arrive(2 + c);
@@ -891,7 +922,8 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     epi_sync();                              // rowidx is read by other threads from here on
     const unsigned lane_t = tmem + ((unsigned)(q * 32) << 16);
     const int S = job.S;
-    const int idxA = sm.rowidx[rA], idxB = sm.rowidx[rB];
+    const int idxA = sm.rowidx[rA], idxB = HALF ? -1 : sm.rowidx[rB];
+    const float (*bias)[TN] = sm.bias[branch];
 
     for (int l = 0; l < nl; ++l) {
       const int kind = ch.layer[l].kind;
@@ -919,11 +951,13 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           for (int g = 0; g < (c ? G1 : G0); ++g) {
             const int col = (c ? R0 + cb * 8 * G1 : cb * 8 * G0) + g * 8 + cq;
             const unsigned* rr = raw + 4 * ((c ? G0 : 0) + g);
-            const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + col);
+            const float2 bi = *reinterpret_cast<const float2*>(bias[l] + col);
             const float a0 = elu_fast(__uint_as_float(rr[0]) + bi.x), a1 = elu_fast(__uint_as_float(rr[1]) + bi.y);
-            const float b0 = elu_fast(__uint_as_float(rr[2]) + bi.x), b1 = elu_fast(__uint_as_float(rr[3]) + bi.y);
             a64_store2(sm.a, rA, col, pack_bf16(a0, a1));
-            a64_store2(sm.a, rB, col, pack_bf16(b0, b1));
+            if constexpr (!HALF) {
+              const float b0 = elu_fast(__uint_as_float(rr[2]) + bi.x), b1 = elu_fast(__uint_as_float(rr[3]) + bi.y);
+              a64_store2(sm.a, rB, col, pack_bf16(b0, b1));
+            }
           }
           fence_async_smem();
           if (c == 1) tc_fence_before();
@@ -938,9 +972,13 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         float xa[8], xb[8];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + c0 + g * 8 + cq);
+          const float2 bi = *reinterpret_cast<const float2*>(bias[l] + c0 + g * 8 + cq);
           xa[2 * g] = __uint_as_float(raw[4 * g + 0]) + bi.x; xa[2 * g + 1] = __uint_as_float(raw[4 * g + 1]) + bi.y;
-          xb[2 * g] = __uint_as_float(raw[4 * g + 2]) + bi.x; xb[2 * g + 1] = __uint_as_float(raw[4 * g + 3]) + bi.y;
+          if constexpr (!HALF) {
+            xb[2 * g] = __uint_as_float(raw[4 * g + 2]) + bi.x; xb[2 * g + 1] = __uint_as_float(raw[4 * g + 3]) + bi.y;
+          } else {
+            xb[2 * g] = 0.f; xb[2 * g + 1] = 0.f;
+          }
         }
         const bool state_seg = (kind == LK_STATE || kind == LK_STATE_REWARD) && cb < 2;
         const bool soft_seg = (kind == LK_STATE_REWARD && cb >= 2) || (kind == LK_PRED && cb < 2);
@@ -950,87 +988,107 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             loa = fminf(loa, xa[i]); hia = fmaxf(hia, xa[i]);
-            lob = fminf(lob, xb[i]); hib = fmaxf(hib, xb[i]);
+            if constexpr (!HALF) { lob = fminf(lob, xb[i]); hib = fmaxf(hib, xb[i]); }
           }
 #pragma unroll
           for (int off = 1; off <= 2; off <<= 1) {
             loa = fminf(loa, __shfl_xor_sync(0xffffffffu, loa, off)); hia = fmaxf(hia, __shfl_xor_sync(0xffffffffu, hia, off));
-            lob = fminf(lob, __shfl_xor_sync(0xffffffffu, lob, off)); hib = fmaxf(hib, __shfl_xor_sync(0xffffffffu, hib, off));
+            if constexpr (!HALF) {
+              lob = fminf(lob, __shfl_xor_sync(0xffffffffu, lob, off)); hib = fmaxf(hib, __shfl_xor_sync(0xffffffffu, hib, off));
+            }
           }
           if ((lane & 3) == 0) {
             sm.part[cb][rA] = make_float4(loa, hia, 0.f, 0.f);
-            sm.part[cb][rB] = make_float4(lob, hib, 0.f, 0.f);
+            if constexpr (!HALF) sm.part[cb][rB] = make_float4(lob, hib, 0.f, 0.f);
           }
         } else if (soft_seg) {
           float ma = -1e30f, mb = -1e30f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { ma = fmaxf(ma, xa[i]); mb = fmaxf(mb, xb[i]); }
+          for (int i = 0; i < 8; ++i) { ma = fmaxf(ma, xa[i]); if constexpr (!HALF) mb = fmaxf(mb, xb[i]); }
           spa.m = ma; spb.m = mb;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const float pos = (float)(((c0 + g * 8 + cq + j) & 63) - S / 2);
-              const float ea = ex2f((xa[2 * g + j] - ma) * 1.4426950408889634f), eb = ex2f((xb[2 * g + j] - mb) * 1.4426950408889634f);
-              spa.z += ea; spa.y = fmaf(pos, ea, spa.y);
-              spb.z += eb; spb.y = fmaf(pos, eb, spb.y);
+              const float pos_c = (float)(((c0 + g * 8 + cq + j) & 63) - S / 2);
+              const float ea = ex2f((xa[2 * g + j] - ma) * 1.4426950408889634f);
+              spa.z += ea; spa.y = fmaf(pos_c, ea, spa.y);
+              if constexpr (!HALF) {
+                const float eb = ex2f((xb[2 * g + j] - mb) * 1.4426950408889634f);
+                spb.z += eb; spb.y = fmaf(pos_c, eb, spb.y);
+              }
             }
-          spa = soft_quad(spa); spb = soft_quad(spb);
+          spa = soft_quad(spa);
+          if constexpr (!HALF) spb = soft_quad(spb);
           if ((lane & 3) == 0) {
             sm.part[cb][rA] = make_float4(spa.m, spa.z, spa.y, 0.f);
-            sm.part[cb][rB] = make_float4(spb.m, spb.z, spb.y, 0.f);
+            if constexpr (!HALF) sm.part[cb][rB] = make_float4(spb.m, spb.z, spb.y, 0.f);
           }
         }
         epi_sync();
         unsigned pend_a[4], pend_b[4];
         bool have_pend = false;
         if (state_seg) {
-          const float4 oa = sm.part[cb ^ 1][rA], ob = sm.part[cb ^ 1][rB], ma4 = sm.part[cb][rA], mb4 = sm.part[cb][rB];
-          const float loa = fminf(ma4.x, oa.x), hia = fmaxf(ma4.y, oa.y), lob = fminf(mb4.x, ob.x), hib = fmaxf(mb4.y, ob.y);
-          float sa = hia - loa, sb = hib - lob;
+          const float4 oa = sm.part[cb ^ 1][rA], ma4 = sm.part[cb][rA];
+          const float loa = fminf(ma4.x, oa.x), hia = fmaxf(ma4.y, oa.y);
+          float sa = hia - loa;
           if (sa < 1e-5f) sa += 1e-5f;
-          if (sb < 1e-5f) sb += 1e-5f;
-          const float ia = 1.f / sa, ib = 1.f / sb;
+          const float ia = 1.f / sa;
+          float lob = 0.f, ib = 0.f;
+          if constexpr (!HALF) {
+            const float4 ob = sm.part[cb ^ 1][rB], mb4 = sm.part[cb][rB];
+            lob = fminf(mb4.x, ob.x);
+            float sb = fmaxf(mb4.y, ob.y) - lob;
+            if (sb < 1e-5f) sb += 1e-5f;
+            ib = 1.f / sb;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             pend_a[g] = pack_bf16((xa[2 * g] - loa) * ia, (xa[2 * g + 1] - loa) * ia);
-            pend_b[g] = pack_bf16((xb[2 * g] - lob) * ib, (xb[2 * g + 1] - lob) * ib);
             a64_store2(sm.a, rA, c0 + g * 8 + cq, pend_a[g]);
-            a64_store2(sm.a, rB, c0 + g * 8 + cq, pend_b[g]);
+            if constexpr (!HALF) {
+              pend_b[g] = pack_bf16((xb[2 * g] - lob) * ib, (xb[2 * g + 1] - lob) * ib);
+              a64_store2(sm.a, rB, c0 + g * 8 + cq, pend_b[g]);
+            } else {
+              pend_b[g] = 0u;
+            }
           }
           have_pend = job.hidden16_dst != nullptr;
         } else if (soft_seg && (cb & 1) == 0) {
           if ((lane & 3) == 0) {
-            const float4 oa = sm.part[cb + 1][rA], ob = sm.part[cb + 1][rB];
             float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
             if (dst) {
+              const float4 oa = sm.part[cb + 1][rA];
               if (idxA >= 0) dst[idxA] = support_scalar(spa, SoftPart{oa.x, oa.y, oa.z});
-              if (idxB >= 0) dst[idxB] = support_scalar(spb, SoftPart{ob.x, ob.y, ob.z});
+              if constexpr (!HALF) {
+                const float4 ob = sm.part[cb + 1][rB];
+                if (idxB >= 0) dst[idxB] = support_scalar(spb, SoftPart{ob.x, ob.y, ob.z});
+              }
             }
           }
         } else if (kind == LK_PRED && cb == 2) {
           const int n = ch.n_policy;
           float ma = -1e30f, mb = -1e30f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { ma = fmaxf(ma, xa[i]); mb = fmaxf(mb, xb[i]); }
+          for (int i = 0; i < 8; ++i) { ma = fmaxf(ma, xa[i]); if constexpr (!HALF) mb = fmaxf(mb, xb[i]); }
 #pragma unroll
           for (int off = 1; off <= 2; off <<= 1) {
             ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, off));
-            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, off));
+            if constexpr (!HALF) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, off));
           }
           float za = 0.f, zb = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             xa[i] = ex2f((xa[i] - ma) * 1.4426950408889634f); za += xa[i];
-            xb[i] = ex2f((xb[i] - mb) * 1.4426950408889634f); zb += xb[i];
+            if constexpr (!HALF) { xb[i] = ex2f((xb[i] - mb) * 1.4426950408889634f); zb += xb[i]; }
           }
 #pragma unroll
           for (int off = 1; off <= 2; off <<= 1) {
             za += __shfl_xor_sync(0xffffffffu, za, off);
-            zb += __shfl_xor_sync(0xffffffffu, zb, off);
+            if constexpr (!HALF) zb += __shfl_xor_sync(0xffffffffu, zb, off);
           }
           if (job.policy_dst) {
-            const float ia = 1.f / za, ib = 1.f / zb;
+            const float ia = 1.f / za, ib = HALF ? 0.f : 1.f / zb;
 #pragma unroll
             for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -1038,7 +1096,9 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
                 const int i = g * 8 + cq + j;
                 if (i < n) {
                   if (idxA >= 0) job.policy_dst[(size_t)idxA * job.pstride + i] = xa[2 * g + j] * ia;
-                  if (idxB >= 0) job.policy_dst[(size_t)idxB * job.pstride + i] = xb[2 * g + j] * ib;
+                  if constexpr (!HALF) {
+                    if (idxB >= 0) job.policy_dst[(size_t)idxB * job.pstride + i] = xb[2 * g + j] * ib;
+                  }
                 }
               }
           }
@@ -1052,7 +1112,9 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (idxA >= 0) *reinterpret_cast<unsigned*>(job.hidden16_dst + (size_t)idxA * SMZ_SP + c0 + g * 8 + cq) = pend_a[g];
-            if (idxB >= 0) *reinterpret_cast<unsigned*>(job.hidden16_dst + (size_t)idxB * SMZ_SP + c0 + g * 8 + cq) = pend_b[g];
+            if constexpr (!HALF) {
+              if (idxB >= 0) *reinterpret_cast<unsigned*>(job.hidden16_dst + (size_t)idxB * SMZ_SP + c0 + g * 8 + cq) = pend_b[g];
+            }
           }
         }
       }
@@ -1410,6 +1472,7 @@ struct SmzBf16Image {
   long long* timeline;    // device debug buffer or null (SMZ_BF16_TIMELINE=1)
   int pipe_rounds;        // 2 (default) or 4 rounds per hidden layer in the pipelined kernel (SMZ_PIPE_ROUNDS)
   int use_m64;            // 64-row tiles: -1 = by batch size (busy CTAs fit one wave of SMs), SMZ_M64=0/1 forces
+  int use_m32;            // 32 leaves per 64-row tile: -1 = while those tiles fit one wave of SMs, SMZ_M32=0/1 forces
   int n_sms;
   int timeline_mega;
   int use_pipe;           // K-pipelined chain for the simulation step (SMZ_NO_PIPE=1 turns it off)
@@ -1466,8 +1529,15 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&im->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || im->n_sms <= 0) im->n_sms = 148;
   }
-  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
-  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  im->use_m32 = getenv("SMZ_M32") ? atoi(getenv("SMZ_M32")) : -1;
+  // the network CTAs share their SMs with the blocks of the tree step that is launched while they run (PDL): ask for the
+  // largest shared-memory carve-out, or the SM is configured for this kernel alone and the tree blocks wait for it to drain
+  for (const void* f : {(const void*)k_bf16_chain_m64<64, false>, (const void*)k_bf16_chain_m64<96, false>,
+                        (const void*)k_bf16_chain_m64<96, true>, (const void*)k_bf16_chain_pipe<2>, (const void*)k_bf16_chain_pipe<4>})
+    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
@@ -1609,12 +1679,15 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
   // 64-row tiles halve the MUFU-bound epilogue per SM as long as the busy CTAs (~trees / 64 + 2) fit one wave
   // (measured on B200, cfg-2 shapes: 8192 trees 267 vs 240 M sims/s, 16384 trees 288 vs 350)
-  const bool m64 = im->use_m64 < 0 ? (n_trees + TM64 - 1) / TM64 + 2 <= im->n_sms : im->use_m64 != 0;
+  // one CTA per tile of the simulation's row array (a.row_top positions, both branches): no idle CTAs of the
+  // "other" branch, so the one-wave condition is on row_top / tile
+  const bool m64 = im->use_m64 < 0 ? a.row_top / TM64 <= im->n_sms : im->use_m64 != 0;
+  const bool m32 = m64 && (im->use_m32 < 0 ? a.row_top / 32 <= im->n_sms : im->use_m32 != 0);
   if (tree_mode == 0 && im->use_pipe && m64) {
-    const dim3 grid64(2 * ((n_trees + TM64 - 1) / TM64));
     const bool uneven = getenv("SMZ_M64_EVEN") == nullptr;     // 96 + 32 columns measured 2.7 % faster than 64 + 64
-    auto* k64 = uneven ? k_bf16_chain_m64<96> : k_bf16_chain_m64<64>;
-    smz_launch(k64, grid64, dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    auto* k64 = m32 ? k_bf16_chain_m64<96, true> : (uneven ? k_bf16_chain_m64<96, false> : k_bf16_chain_m64<64, false>);
+    smz_launch(k64, dim3(a.row_top / (m32 ? 32 : TM64)), dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after,
+               im->chain_dyn, job, sim);
     return;
   }
   if (tree_mode == 0 && im->use_pipe) {
