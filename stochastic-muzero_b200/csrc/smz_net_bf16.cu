@@ -765,8 +765,7 @@ __device__ __forceinline__ void a64_store2(unsigned char* a, int row, int col, u
 // the branch counts — one L2 round trip after the dependency wait — and no CTA is launched for an empty tile of
 // the "other" branch.  The first weight tile of BOTH chains is prefetched before the wait.
 template <int R0, bool HALF>
-__global__ void __maxnreg__(80)
-k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+__device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& chain0, const Chain& chain1, const Job& job, int sim) {
   extern __shared__ unsigned char smem_raw[];
   Smem64& sm = *reinterpret_cast<Smem64*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int TV = HALF ? 32 : 64;       // leaves per tile
@@ -867,6 +866,7 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       for (int c = 0; c < 2; ++c) {
         nb_sync(2 + c);
         if (tl && c == 1) tl[1 + l * 4 + 0] = clock64();       // last round of the layer is in the A operand
+        if (tl && c == 0 && l == 3) tl[1 + 4 * MAXL + 10] = clock64();
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -876,6 +876,7 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
                      k > 0 ? 1u : 0u);
         }
         __syncwarp();
+        if (tl && c == 0 && l == 3) tl[1 + 4 * MAXL + 11] = clock64();
       }
       if (lane == 0) umma_commit(&sm.dbar[l & 1]);
       if (tl) tl[1 + l * 4 + 1] = clock64();
@@ -945,6 +946,8 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           tmem_ld16x256_x1(lane_t + dcol + 96 + cb * 8, raw + 12);
         }
         tmem_wait_ld();
+        const bool fine = tl && warp == 0 && l == 2;
+        if (fine) tl[1 + 4 * MAXL + 2] = clock64();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -959,9 +962,12 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
               a64_store2(sm.a, rB, col, pack_bf16(b0, b1));
             }
           }
+          if (fine) tl[1 + 4 * MAXL + 3 + 3 * c] = clock64();
           fence_async_smem();
           if (c == 1) tc_fence_before();
+          if (fine) tl[1 + 4 * MAXL + 4 + 3 * c] = clock64();
           nb_arrive(2 + c);
+          if (fine) tl[1 + 4 * MAXL + 5 + 3 * c] = clock64();
         }
       } else {
         // head layer: this warp owns the 32-column block cb of its 16 rows (fragment: 4 groups x {rowA, rowB} x 2 columns)
@@ -1126,6 +1132,19 @@ k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TN) : "memory");
   }
+}
+
+template <int R0>
+__global__ void __launch_bounds__(NPIPE, 1)
+k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  chain_m64_body<R0, false>(a, chain0, chain1, job, sim);
+}
+// 32-leaf tiles: 80 registers per thread, so that a block of the tree step (4 warps x 88 registers) still fits next to
+// the 17 warps of this CTA in every SM sub-partition (16 K registers each; sub-partition 0 holds 5 of the 17 warps) —
+// with one network CTA on nearly every SM the tree step launched under it (PDL) has nowhere else to go
+__global__ void __maxnreg__(80)
+k_bf16_chain_m32(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  chain_m64_body<96, true>(a, chain0, chain1, job, sim);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1529,14 +1548,15 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&im->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || im->n_sms <= 0) im->n_sms = 148;
   }
-  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
-  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
-  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m64<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_m32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem64) + 1024);
   im->use_m32 = getenv("SMZ_M32") ? atoi(getenv("SMZ_M32")) : -1;
-  // the network CTAs share their SMs with the blocks of the tree step that is launched while they run (PDL): ask for the
-  // largest shared-memory carve-out, or the SM is configured for this kernel alone and the tree blocks wait for it to drain
-  for (const void* f : {(const void*)k_bf16_chain_m64<64, false>, (const void*)k_bf16_chain_m64<96, false>,
-                        (const void*)k_bf16_chain_m64<96, true>, (const void*)k_bf16_chain_pipe<2>, (const void*)k_bf16_chain_pipe<4>})
+  // The small-batch network CTAs share their SMs with the blocks of the shared-memory tree step that is launched while
+  // they run (PDL): both kernels ask for the largest shared-memory carve-out, otherwise an SM is configured for the first
+  // of them alone and the other's blocks wait for it to drain (measured: 156 vs 176 M sims/s on cfg2).  NOT set on the
+  // arena-only tree kernels of the large batches — they live on the L1 (cfg4: 534 -> 480 M sims/s with it).
+  for (const void* f : {(const void*)k_bf16_chain_m64<64>, (const void*)k_bf16_chain_m64<96>, (const void*)k_bf16_chain_m32})
     cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
@@ -1564,9 +1584,16 @@ void smz_bf16_destroy(SmzBf16Image* im) {
       if (im->timeline_mega)
         fprintf(stderr, "  persistent kernel, last simulation: tree phase %lld | barrier %lld | sort+gather %lld | to first layer +%lld\n",
                 h[0] - t[0], h[1] - h[0], h[2] - h[1], t[1] - h[2]);
-      else if (h[0] && !h[1])
+      else if (h[0] && !h[1]) {
         fprintf(stderr, "  pipelined kernel: dependency wait returned at +%lld (A operand of layer 0 complete %lld cycles later)\n",
                 h[0] - t[0], t[1] - h[0]);
+        if (h[2])
+          fprintf(stderr, "  layer 2, epilogue warp 0: accumulator seen -> loaded %lld | round 0: math+stores %lld, fence %lld, arrive %lld | "
+                  "round 1: math+stores %lld, fence %lld, arrive %lld\n  layer 3, issuer: round 0 in operand +%lld after the layer-2 epilogue "
+                  "started; its K-steps issued in %lld; round 1 seen %lld later\n",
+                  h[2] - t[1 + 2 * 4 + 2], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7],
+                  h[10] - t[1 + 2 * 4 + 2], h[11] - h[10], t[1 + 3 * 4] - h[11]);
+      }
       else
       for (int k = 0; k < 2; ++k, h += 8)
         fprintf(stderr, "  %s head (thread 0): load+bias -> partials %lld | barrier %lld | finish %lld | fence+barrier %lld\n",
@@ -1685,7 +1712,7 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   const bool m32 = m64 && (im->use_m32 < 0 ? a.row_top / 32 <= im->n_sms : im->use_m32 != 0);
   if (tree_mode == 0 && im->use_pipe && m64) {
     const bool uneven = getenv("SMZ_M64_EVEN") == nullptr;     // 96 + 32 columns measured 2.7 % faster than 64 + 64
-    auto* k64 = m32 ? k_bf16_chain_m64<96, true> : (uneven ? k_bf16_chain_m64<96, false> : k_bf16_chain_m64<64, false>);
+    auto* k64 = m32 ? k_bf16_chain_m32 : (uneven ? k_bf16_chain_m64<96> : k_bf16_chain_m64<64>);
     smz_launch(k64, dim3(a.row_top / (m32 ? 32 : TM64)), dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after,
                im->chain_dyn, job, sim);
     return;

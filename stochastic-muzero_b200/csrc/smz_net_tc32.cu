@@ -46,6 +46,15 @@ constexpr int POL_OFF = 64;             // column of the second head inside a he
 constexpr int R0 = 96;                  // columns of the first hidden-layer round (96 + 32: two K-steps left for the tail)
 // InstrDescriptor: D = f32 (bit 4), A = B = f16 (format 0 at bits 7, 10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr unsigned IDESC = (1u << 4) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
+// Split (fp32-grade) mode: the hi and lo parts of the activations are STACKED along M — one 128-row A operand whose rows
+// 32q + i hold the hi part and rows 32q + 16 + i the lo part of leaf 16q + i.  tcgen05.mma costs the same for M = 64 and
+// M = 128 (max(M, 128) N / 256 cycles), so (hi; lo) x W_hi and (hi; lo) x W_lo — all FOUR partial products, lo x lo
+// included — take two instructions per K-step instead of three.  The accumulator of M = 128 keeps row r in TMEM lane r:
+// a warp reads the hi rows of its leaves with one 16x256b load (lanes 32q ..) and the lo rows with a second one
+// (lanes 32q + 16 ..), same fragment positions, and adds them in registers.
+constexpr int TMS = 128;                // A rows of the stacked operand
+constexpr int CHUNK_AS = TMS * 16;      // its LBO
+constexpr unsigned IDESC_S = (1u << 4) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TMS >> 4) << 24);
 
 enum LayerKind { LK_HIDDEN = 0, LK_STATE = 1, LK_STATE_REWARD = 2, LK_PRED = 3, LK_CODE = 4 };
 // IN_FEAT: the MLP heads of the vision family (neural_network_vision_model.py: 147 -> H -> .. -> S / A after the 1x1
@@ -104,12 +113,13 @@ struct SmemT {
                             // passed the named-barrier arrivals that follow its reads (the accumulator wait implies them)
 };
 
+template <bool STACKED>
 __device__ __forceinline__ void umma(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
+      "l"(adesc), "l"(bdesc), "r"(STACKED ? IDESC_S : IDESC), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void epi_sync() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
@@ -134,9 +144,10 @@ __device__ __forceinline__ void sts16(unsigned char* p, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void sts4(unsigned char* p, unsigned v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(s32(p)), "r"(v) : "memory"); }
-// two halves at (row, col), col even, of one operand part
+// two halves at (operand row, col), col even; CH = bytes between K-chunks (CHUNK_A, or CHUNK_AS for the stacked operand)
+template <int CH>
 __device__ __forceinline__ unsigned char* a_at(unsigned char* part, int row, int col) {
-  return part + (col >> 3) * CHUNK_A + row * 16 + (col & 7) * 2;
+  return part + (col >> 3) * CH + row * 16 + (col & 7) * 2;
 }
 
 __device__ __forceinline__ unsigned pack_f16(float lo, float hi) {
@@ -178,13 +189,16 @@ __global__ void __launch_bounds__(NTHR, 1)
 k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   constexpr bool SPLIT = NPROD == 3;
   constexpr int ROWQ = SPLIT ? 16 : 8;            // 16-byte pieces per arena row
+  constexpr int CH = SPLIT ? CHUNK_AS : CHUNK_A;  // bytes between K-chunks of the A operand (SPLIT: 128 stacked rows)
   extern __shared__ unsigned char smem_raw[];
   SmemT<KA>& sm = *reinterpret_cast<SmemT<KA>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer_warp = warp == NEPI / 32;
   const int q = warp & 3;                  // TMEM lane quarter: tile rows 16q .. 16q+15
   const int cb = (warp >> 2) & 3;          // head layers: 32-column block; hidden layers: slice of a round
-  const int rA = 16 * q + (lane >> 2), rB = rA + 8;     // the two tile rows of this thread's accumulator fragment
+  const int rA = 16 * q + (lane >> 2), rB = rA + 8;     // the two tile rows (leaves) of this thread's accumulator fragment
+  // operand rows of those leaves: SPLIT stacks hi rows at 32q + i and lo rows at 32q + 16 + i (see IDESC_S)
+  const int oA = SPLIT ? 32 * q + (lane >> 2) : rA, oB = oA + 8;
   const int cq = 2 * (lane & 3);           // column offset inside an 8-column group
 
   // gather launches use a static split: CTAs [0, T) serve the afterstate rows, [T, 2T) the dynamics rows, so the
@@ -316,7 +330,7 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 
   if (is_issuer_warp) {
     // =========================== issuer warp: weight ring + 3 x tcgen05.mma per K-step ==========================
-    const unsigned long long ad_hi = umma_desc(s32(sm.a[0]), CHUNK_A, 128), ad_lo = umma_desc(s32(sm.a[1]), CHUNK_A, 128);
+    const unsigned long long ad = umma_desc(s32(sm.a[0]), CH, 128);
     for (int l = 0; l < nl; ++l) {
       const int nk = ch.layer[l].K / 16;
       mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
@@ -330,13 +344,10 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 #pragma unroll
           for (int k = 0; k < KA / 16; ++k)
             if (k >= (c ? R0 / 16 : 0) && k < (c ? KA / 16 : R0 / 16) && k < nk) {
-              const unsigned long long oa = (unsigned long long)(k * ((2 * CHUNK_A) >> 4));
+              const unsigned long long oa = (unsigned long long)(k * ((2 * CH) >> 4));
               const unsigned long long ow = (unsigned long long)(k * ((2 * CHUNK_W) >> 4));
-              umma(d, ad_hi + oa, bd_hi + ow, k > 0 ? 1u : 0u);
-              if (SPLIT) {
-                umma(d, ad_lo + oa, bd_hi + ow, 1u);
-                umma(d, ad_hi + oa, bd_lo + ow, 1u);
-              }
+              umma<SPLIT>(d, ad + oa, bd_hi + ow, k > 0 ? 1u : 0u);
+              if (SPLIT) umma<SPLIT>(d, ad + oa, bd_lo + ow, 1u);
             }
         }
         __syncwarp();
@@ -354,16 +365,18 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     {
       const bool valid = tile * TM + srow < count;
       const uint4 z = make_uint4(0, 0, 0, 0);
-      sts16(sm.a[0] + skc * CHUNK_A + srow * 16, valid ? h0 : z);
-      if (SPLIT) sts16(sm.a[1] + skc * CHUNK_A + srow * 16, valid ? l0 : z);
+      unsigned char* const ph = sm.a[0] + (SPLIT ? 32 * (srow >> 4) + (srow & 15) : srow) * 16;   // hi row of the staged leaf
+      unsigned char* const pl = ph + 16 * 16;                                                      // its lo row (SPLIT)
+      sts16(ph + skc * CH, valid ? h0 : z);
+      if (SPLIT) sts16(pl + skc * CH, valid ? l0 : z);
       if (job.input_kind == IN_OBS || job.input_kind == IN_FEAT) {
         if ((skc + 8) * 8 < ch.kin) {
-          sts16(sm.a[0] + (skc + 8) * CHUNK_A + srow * 16, valid ? h1 : z);
-          if (SPLIT) sts16(sm.a[1] + (skc + 8) * CHUNK_A + srow * 16, valid ? l1 : z);
+          sts16(ph + (skc + 8) * CH, valid ? h1 : z);
+          if (SPLIT) sts16(pl + (skc + 8) * CH, valid ? l1 : z);
         }
         if (KA > 128 && (skc + 16) * 8 < ch.kin) {
-          sts16(sm.a[0] + (skc + 16) * CHUNK_A + srow * 16, valid ? h2 : z);
-          if (SPLIT) sts16(sm.a[1] + (skc + 16) * CHUNK_A + srow * 16, valid ? l2 : z);
+          sts16(ph + (skc + 16) * CH, valid ? h2 : z);
+          if (SPLIT) sts16(pl + (skc + 16) * CH, valid ? l2 : z);
         }
       } else if (skc < ch.onehot_pad / 8) {              // one-hot action / code: a single fp16 1.0 in the hi part
         const int act = valid ? sact : -1;
@@ -372,8 +385,8 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           const int j = act - skc * 8;
           w4[j >> 1] = (j & 1) ? 0x3C000000u : 0x00003C00u;
         }
-        sts16(sm.a[0] + (8 + skc) * CHUNK_A + srow * 16, make_uint4(w4[0], w4[1], w4[2], w4[3]));
-        if (SPLIT) sts16(sm.a[1] + (8 + skc) * CHUNK_A + srow * 16, z);
+        sts16(ph + (8 + skc) * CH, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+        if (SPLIT) sts16(pl + (8 + skc) * CH, z);
       }
       if (skc == 0) sm.rowidx[srow] = valid ? sidx : -1;
     }
@@ -382,6 +395,7 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     mbar_wait(&sm.bbar, 0);
     epi_sync();                              // rowidx is read by other threads from here on
     const unsigned lane_t = tmem + ((unsigned)(q * 32) << 16);
+    const unsigned lane_lo = lane_t + (16u << 16);
     const int S = job.S;
     const int idxA = sm.rowidx[rA], idxB = sm.rowidx[rB];
 
@@ -399,6 +413,15 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         tmem_ld16x256_x2(lane_t + dcol + cb * 24, raw);
         tmem_ld16x256_x1(lane_t + dcol + cb * 24 + 16, raw + 8);
         tmem_ld16x256_x1(lane_t + dcol + 96 + cb * 8, raw + 12);
+        if (SPLIT) {                      // the lo rows' accumulators: lanes + 16, same fragment positions
+          unsigned rlo[4 * (G0 + G1)];
+          tmem_ld16x256_x2(lane_lo + dcol + cb * 24, rlo);
+          tmem_ld16x256_x1(lane_lo + dcol + cb * 24 + 16, rlo + 8);
+          tmem_ld16x256_x1(lane_lo + dcol + 96 + cb * 8, rlo + 12);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 4 * (G0 + G1); ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(rlo[i]));
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -412,12 +435,12 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             unsigned hi, lo;
             if (SPLIT) {
               split2(a0, a1, hi, lo);
-              sts4(a_at(sm.a[0], rA, col), hi); sts4(a_at(sm.a[1], rA, col), lo);
+              sts4(a_at<CH>(sm.a[0], oA, col), hi); sts4(a_at<CH>(sm.a[0], oA + 16, col), lo);
               split2(b0, b1, hi, lo);
-              sts4(a_at(sm.a[0], rB, col), hi); sts4(a_at(sm.a[1], rB, col), lo);
+              sts4(a_at<CH>(sm.a[0], oB, col), hi); sts4(a_at<CH>(sm.a[0], oB + 16, col), lo);
             } else {
-              sts4(a_at(sm.a[0], rA, col), pack_f16(a0, a1));
-              sts4(a_at(sm.a[0], rB, col), pack_f16(b0, b1));
+              sts4(a_at<CH>(sm.a[0], oA, col), pack_f16(a0, a1));
+              sts4(a_at<CH>(sm.a[0], oB, col), pack_f16(b0, b1));
             }
           }
           fence_async_smem();
@@ -431,6 +454,13 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         const int c0 = cb * 32;
         unsigned raw[16];
         tmem_ld16x256_x4(lane_t + dcol + c0, raw);
+        if (SPLIT) {
+          unsigned rlo[16];
+          tmem_ld16x256_x4(lane_lo + dcol + c0, rlo);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(rlo[i]));
+        }
         tmem_wait_ld();
         float xa[8], xb[8];
 #pragma unroll
@@ -493,13 +523,13 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             if (SPLIT) {
               split2(a0, a1, pend_ah[g], pend_al[g]);
               split2(b0, b1, pend_bh[g], pend_bl[g]);
-              sts4(a_at(sm.a[1], rA, col), pend_al[g]);
-              sts4(a_at(sm.a[1], rB, col), pend_bl[g]);
+              sts4(a_at<CH>(sm.a[0], oA + 16, col), pend_al[g]);
+              sts4(a_at<CH>(sm.a[0], oB + 16, col), pend_bl[g]);
             } else {
               pend_ah[g] = pack_f16(a0, a1); pend_bh[g] = pack_f16(b0, b1);
             }
-            sts4(a_at(sm.a[0], rA, col), pend_ah[g]);
-            sts4(a_at(sm.a[0], rB, col), pend_bh[g]);
+            sts4(a_at<CH>(sm.a[0], oA, col), pend_ah[g]);
+            sts4(a_at<CH>(sm.a[0], oB, col), pend_bh[g]);
             if (job.hidden_dst) {
               if (idxA >= 0) *reinterpret_cast<float2*>(job.hidden_dst + (size_t)idxA * SMZ_SP + col) = make_float2(a0, a1);
               if (idxB >= 0) *reinterpret_cast<float2*>(job.hidden_dst + (size_t)idxB * SMZ_SP + col) = make_float2(b0, b1);

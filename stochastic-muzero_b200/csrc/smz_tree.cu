@@ -354,9 +354,7 @@ void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim
                                       a, n_trees, sim, rcp_entries(a))));
     return;
   }
-  SMZ_DISPATCH_G(lanes, (cudaFuncSetAttribute((const void*)k_backup_select<G>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                              cudaSharedmemCarveoutMaxShared),
-                         smz_launch(k_backup_select<G>, dim3(grid_for<G>(n_trees, kThreads)), dim3(kThreads), 0, s, pdl,
+  SMZ_DISPATCH_G(lanes, (smz_launch(k_backup_select<G>, dim3(grid_for<G>(n_trees, kThreads)), dim3(kThreads), 0, s, pdl,
                                     a, n_trees, sim)));
 }
 
