@@ -74,6 +74,7 @@ struct Job {
   int pstride;
   int S;
   long long* timeline;      // debug: clock64 stamps of CTA 0 (null = off)
+  int stream_all;           // debug (SMZ_STREAM_ALL=1): stream every layer's weight tile even when it is already resident
 };
 
 struct Smem {
@@ -852,15 +853,30 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
 
   if (is_issuer_warp) {
     const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A64, 128);
-    if (nl > 1) {                              // layer 1 replaces the unused chain's prefetched tile
-      mbar_wait(&sm.wbar[(1 + branch) & 1], 0);
-      if (lane == 0) load_weights(ch, 1, (1 + branch) & 1);
+    // Weight ring.  The hidden layers of a network share ONE weight tile (the reference ties them, mlp:31-37): a tile
+    // that is already resident in its slot is not streamed again — 6 bulk copies per chain instead of 12.
+    // nfill / nseen = fills issued to / waited for on each slot; slot `branch` holds layer 0 (fill 0, prefetched),
+    // the other slot's fill 0 was the unused chain's layer 0 and is replaced by layer 1 as soon as it has landed.
+    unsigned nfill[2] = {1u, 1u}, nseen[2] = {0u, 0u};
+    const __nv_bfloat16* resident[2];
+    resident[branch] = ch.layer[0].w;
+    resident[branch ^ 1] = nullptr;
+    if (nl > 1) {
+      const int s1 = branch ^ 1;
+      mbar_wait(&sm.wbar[s1], 0);
+      nseen[s1] = 1u;
+      if (lane == 0) load_weights(ch, 1, s1);
+      nfill[s1] = 2u;
+      resident[s1] = ch.layer[1].w;
       __syncwarp();
     }
     for (int l = 0; l < nl; ++l) {
       const int nk = ch.layer[l].K / 16;
       const int slot = (l + branch) & 1;
-      mbar_wait(&sm.wbar[slot], ((l + 1) >> 1) & 1);
+      if (nseen[slot] < nfill[slot]) {
+        mbar_wait(&sm.wbar[slot], nseen[slot] & 1u);
+        ++nseen[slot];
+      }
       const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
       for (int c = 0; c < 2; ++c) {
@@ -881,9 +897,11 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
       if (lane == 0) umma_commit(&sm.dbar[l & 1]);
       if (tl) tl[1 + l * 4 + 1] = clock64();
       __syncwarp();
-      if (l + 2 < nl) {
-        mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
+      if (l + 2 < nl && (resident[slot] != ch.layer[l + 2].w || job.stream_all)) {
+        mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);            // the slot is free once these MMAs have completed
         if (lane == 0) load_weights(ch, l + 2, slot);
+        ++nfill[slot];
+        resident[slot] = ch.layer[l + 2].w;
         __syncwarp();
       }
     }
@@ -1703,6 +1721,7 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   job.hidden16_dst = reinterpret_cast<__nv_bfloat16*>(a.hidden) + (size_t)(sim + 1) * a.B * SMZ_SP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   job.timeline = im->timeline;
+  job.stream_all = getenv("SMZ_STREAM_ALL") != nullptr;
   const dim3 grid(2 * ((n_trees + TM - 1) / TM)), block(NTHREADS);
   // 64-row tiles halve the MUFU-bound epilogue per SM as long as the busy CTAs (~trees / 64 + 2) fit one wave
   // (measured on B200, cfg-2 shapes: 8192 trees 267 vs 240 M sims/s, 16384 trees 288 vs 350)
