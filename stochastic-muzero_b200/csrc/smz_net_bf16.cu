@@ -947,13 +947,22 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
     for (int l = 0; l < nl; ++l) {
       const int kind = ch.layer[l].kind;
       const unsigned dcol = (unsigned)((l & 1) * TN);
+      // hidden layers: this warp's bias pairs are fetched before the accumulator wait (the asm volatile stores below
+      // are compiler barriers: a load placed after one of them waits for it)
+      constexpr int G0 = R0 / 32, G1 = (TN - R0) / 32;          // 8-column groups per warp in round 0 / 1
+      float2 bi[G0 + G1];
+      if (kind == LK_HIDDEN) {
+#pragma unroll
+        for (int g = 0; g < G0 + G1; ++g)
+          bi[g] = *reinterpret_cast<const float2*>(bias[l] + (g < G0 ? cb * 8 * G0 + g * 8 : R0 + cb * 8 * G1 + (g - G0) * 8) + cq);
+      }
       mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
       if (tl && warp == 0) tl[1 + l * 4 + 2] = clock64();
       __syncwarp();
       tc_fence_after();
       if (kind == LK_HIDDEN) {
-        // two rounds: columns [0, R0) and [R0, 128); this warp owns a quarter of each round for its 16 rows
-        constexpr int G0 = R0 / 32, G1 = (TN - R0) / 32;          // 8-column groups per warp in round 0 / 1
+        // two rounds: columns [0, R0) and [R0, 128); this warp owns a quarter of each round for its 16 rows.  All the
+        // arithmetic of both rounds first (independent chains: the MUFU latencies overlap), then stores + fence per round.
         unsigned raw[4 * (G0 + G1)];
         if constexpr (R0 == 64) {
           tmem_ld16x256_x2(lane_t + dcol + cb * 16, raw);
@@ -966,19 +975,20 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
         tmem_wait_ld();
         const bool fine = tl && warp == 0 && l == 2;
         if (fine) tl[1 + 4 * MAXL + 2] = clock64();
+        unsigned pa[G0 + G1], pb[G0 + G1];
+#pragma unroll
+        for (int g = 0; g < G0 + G1; ++g) {
+          const unsigned* rr = raw + 4 * g;
+          pa[g] = pack_bf16(elu_fast(__uint_as_float(rr[0]) + bi[g].x), elu_fast(__uint_as_float(rr[1]) + bi[g].y));
+          if constexpr (!HALF) pb[g] = pack_bf16(elu_fast(__uint_as_float(rr[2]) + bi[g].x), elu_fast(__uint_as_float(rr[3]) + bi[g].y));
+        }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int g = 0; g < (c ? G1 : G0); ++g) {
             const int col = (c ? R0 + cb * 8 * G1 : cb * 8 * G0) + g * 8 + cq;
-            const unsigned* rr = raw + 4 * ((c ? G0 : 0) + g);
-            const float2 bi = *reinterpret_cast<const float2*>(bias[l] + col);
-            const float a0 = elu_fast(__uint_as_float(rr[0]) + bi.x), a1 = elu_fast(__uint_as_float(rr[1]) + bi.y);
-            a64_store2(sm.a, rA, col, pack_bf16(a0, a1));
-            if constexpr (!HALF) {
-              const float b0 = elu_fast(__uint_as_float(rr[2]) + bi.x), b1 = elu_fast(__uint_as_float(rr[3]) + bi.y);
-              a64_store2(sm.a, rB, col, pack_bf16(b0, b1));
-            }
+            a64_store2(sm.a, rA, col, pa[(c ? G0 : 0) + g]);
+            if constexpr (!HALF) a64_store2(sm.a, rB, col, pb[(c ? G0 : 0) + g]);
           }
           if (fine) tl[1 + 4 * MAXL + 3 + 3 * c] = clock64();
           fence_async_smem();

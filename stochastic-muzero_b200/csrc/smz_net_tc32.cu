@@ -403,12 +403,21 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       const int kind = ch.layer[l].kind;
       const unsigned dcol = (unsigned)((l & 1) * TN);
       const float isc = ch.inv_scale[l];
+      // hidden layers: this warp's bias pairs are fetched before the accumulator wait (the asm volatile stores below are
+      // compiler barriers: a load placed after one of them waits for it)
+      constexpr int G0 = R0 / 32, G1 = (TN - R0) / 32;          // 8-column groups per warp in round 0 / 1
+      float2 bi[G0 + G1];
+      if (kind == LK_HIDDEN) {
+#pragma unroll
+        for (int g = 0; g < G0 + G1; ++g)
+          bi[g] = *reinterpret_cast<const float2*>(sm.bias[l] + (g < G0 ? cb * 8 * G0 + g * 8 : R0 + cb * 8 * G1 + (g - G0) * 8) + cq);
+      }
       mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       if (kind == LK_HIDDEN) {
-        // two rounds: columns [0, 96) and [96, 128); this warp owns a quarter of each round for its 16 rows
-        constexpr int G0 = R0 / 32, G1 = (TN - R0) / 32;          // 8-column groups per warp in round 0 / 1
+        // two rounds: columns [0, 96) and [96, 128); this warp owns a quarter of each round for its 16 rows.  All the
+        // arithmetic of both rounds first (independent chains), then stores + fence per round.
         unsigned raw[4 * (G0 + G1)];
         tmem_ld16x256_x2(lane_t + dcol + cb * 24, raw);
         tmem_ld16x256_x1(lane_t + dcol + cb * 24 + 16, raw + 8);
@@ -423,24 +432,30 @@ k_tc32_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           for (int i = 0; i < 4 * (G0 + G1); ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(rlo[i]));
         }
         tmem_wait_ld();
+        unsigned ah[G0 + G1], al[G0 + G1], bh[G0 + G1], bl[G0 + G1];
+#pragma unroll
+        for (int g = 0; g < G0 + G1; ++g) {
+          const unsigned* rr = raw + 4 * g;
+          const float a0 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[0]), isc, bi[g].x)), a1 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[1]), isc, bi[g].y));
+          const float b0 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[2]), isc, bi[g].x)), b1 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[3]), isc, bi[g].y));
+          if (SPLIT) {
+            split2(a0, a1, ah[g], al[g]);
+            split2(b0, b1, bh[g], bl[g]);
+          } else {
+            ah[g] = pack_f16(a0, a1); bh[g] = pack_f16(b0, b1);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int g = 0; g < (c ? G1 : G0); ++g) {
             const int col = (c ? R0 + cb * 8 * G1 : cb * 8 * G0) + g * 8 + cq;
-            const unsigned* rr = raw + 4 * ((c ? G0 : 0) + g);
-            const float2 bi = *reinterpret_cast<const float2*>(sm.bias[l] + col);
-            const float a0 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[0]), isc, bi.x)), a1 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[1]), isc, bi.y));
-            const float b0 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[2]), isc, bi.x)), b1 = act32<EXACT, RELU>(fmaf(__uint_as_float(rr[3]), isc, bi.y));
-            unsigned hi, lo;
+            const int i = (c ? G0 : 0) + g;
+            sts4(a_at<CH>(sm.a[0], oA, col), ah[i]);
+            sts4(a_at<CH>(sm.a[0], oB, col), bh[i]);
             if (SPLIT) {
-              split2(a0, a1, hi, lo);
-              sts4(a_at<CH>(sm.a[0], oA, col), hi); sts4(a_at<CH>(sm.a[0], oA + 16, col), lo);
-              split2(b0, b1, hi, lo);
-              sts4(a_at<CH>(sm.a[0], oB, col), hi); sts4(a_at<CH>(sm.a[0], oB + 16, col), lo);
-            } else {
-              sts4(a_at<CH>(sm.a[0], oA, col), pack_f16(a0, a1));
-              sts4(a_at<CH>(sm.a[0], oB, col), pack_f16(b0, b1));
+              sts4(a_at<CH>(sm.a[0], oA + 16, col), al[i]);
+              sts4(a_at<CH>(sm.a[0], oB + 16, col), bl[i]);
             }
           }
           fence_async_smem();
