@@ -1588,8 +1588,8 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
     cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
-    cudaMalloc(&im->timeline, (1 + 4 * MAXL + 16) * sizeof(long long));
-    cudaMemset(im->timeline, 0, (1 + 4 * MAXL + 16) * sizeof(long long));
+    cudaMalloc(&im->timeline, (1 + 4 * MAXL + 32) * sizeof(long long));
+    cudaMemset(im->timeline, 0, (1 + 4 * MAXL + 32) * sizeof(long long));
   }
   cudaFuncSetAttribute((const void*)k_bf16_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
   cudaFuncSetAttribute((const void*)k_bf16_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, im->smem_bytes);
@@ -1601,7 +1601,7 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
 void smz_bf16_destroy(SmzBf16Image* im) {
   if (!im) return;
   if (im->timeline) {
-    long long t[1 + 4 * MAXL + 16];
+    long long t[1 + 4 * MAXL + 32];
     if (cudaMemcpy(t, im->timeline, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "smz bf16 timeline (cycles, CTA 0 of the last simulation step):\n");
       for (int l = 0; l < MAXL && t[1 + l * 4 + 3]; ++l)

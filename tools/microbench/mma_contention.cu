@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(544, 1) k(int mode, int n_mma, const unsigned 
     mbar_wait(&bar, 0);
     const long long t2 = clock64();
     if (lane == 0) { out[0] = t1 - t0; out[1] = t2 - t0; stop = 1; }
+    __syncwarp();
+    if (mode & 32) asm volatile("bar.sync 5, 544;" ::: "memory");
   } else {
     const int q = warp & 3, cb = warp >> 2;
     const unsigned lane_t = tmem_base + ((unsigned)(q * 32) << 16) + 256 + cb * 32;
@@ -73,8 +75,15 @@ __global__ void __launch_bounds__(544, 1) k(int mode, int n_mma, const unsigned 
         }
       }
     }
-    while (!stop && it < 100000) {
+    if (mode & 32) { asm volatile("bar.sync 5, 544;" ::: "memory"); }      // truly idle: parked until the issuer joins the barrier
+    float fa = (float)tid, fb = 1.0001f;
+    while (!(mode & 32) && !stop && it < 100000) {
       ++it;
+      if (mode & 64) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) fa = fmaf(fa, fb, 0.5f);
+        if (fa == 123.f) acc++;
+      }
       if (mode & 1) {
         const int rA = 16 * q + (lane >> 2);
 #pragma unroll
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(544, 1) k(int mode, int n_mma, const unsigned 
                      : "=r"(ok) : "r"(s32(&never)), "r"(0u) : "memory");
         acc += ok;
       }
-      if (!(mode & 19)) __nanosleep(200);
+      if (!(mode & (19 | 64))) __nanosleep(200);
     }
     if (acc == 0x12345678u) out[3] = acc;
   }
@@ -108,10 +117,10 @@ int main() {
   unsigned char* g; cudaMalloc(&g, 8 * 32768); cudaMemset(g, 0, 8 * 32768);
   const int smem = 98304 + 1024;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const char* names[] = {"idle", "st.shared", "tcgen05.ld", "st.shared + tcgen05.ld", "bulk copies", "st.shared + fence.proxy.async",
-                         "everything", "mbarrier.try_wait spin"};
-  const int modes[] = {0, 1, 2, 3, 4, 9, 15, 16};
-  for (int m = 0; m < 7; ++m)
+  const char* names[] = {"napping (nanosleep 200)", "st.shared", "tcgen05.ld", "st.shared + tcgen05.ld", "bulk copies", "st.shared + fence.proxy.async",
+                         "parked at a barrier", "busy FMA loops"};
+  const int modes[] = {0, 1, 2, 3, 4, 9, 32, 64};
+  for (int m = 0; m < 8; ++m)
     for (int n : {8, 96}) {
       k<<<1, 544, smem>>>(modes[m], n, g, d);
       cudaError_t e = cudaDeviceSynchronize();
