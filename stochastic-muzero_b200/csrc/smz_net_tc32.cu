@@ -3,9 +3,11 @@
 // The reference computes the five inference functions in fp32 (muzero_model.py:802-909, use_amp=False;
 // neural_network_mlp_model.py:5-250).  tcgen05.mma has no fp32 operand type, so every fp32 operand is split into
 // two fp16 numbers, x = hi + lo with hi = RN16(x), lo = RN16(x - hi) (22 significand bits; the weights are first
-// scaled by a power of two per layer so that their lo parts stay normal), and every K-step issues THREE
-// tcgen05.mma.kind::f16 into the same fp32 TMEM accumulator:
-//       D += A_hi * W_hi   +   A_lo * W_hi   +   A_hi * W_lo          (the dropped A_lo * W_lo term is ~2^-22 relative)
+// scaled by a power of two per layer so that their lo parts stay normal).  The hi and lo parts of the ACTIVATIONS are
+// stacked along M (one 128-row A operand: tcgen05.mma costs the same for M = 64 and M = 128), so every K-step issues
+// TWO tcgen05.mma.kind::f16 into one fp32 TMEM accumulator of 128 lanes:
+//       D[hi rows] += A_hi * W_hi + A_hi * W_lo          D[lo rows] += A_lo * W_hi + A_lo * W_lo
+// and the epilogue adds the two halves in registers — all four partial products (see IDESC_S below).
 // fp16 x fp16 products are exact in the fp32 accumulator, so a layer's pre-activations carry ~2^-22 relative error —
 // the same order as the fp32 reference's own summation error (a numpy emulation of exactly this scheme reproduces the
 // reference's outputs on tests/golden/net_*.npz to 2.4e-7; the CUDA-core fp32 kernel is at 2.9e-7).  Bias, ELU, the
@@ -14,7 +16,7 @@
 // Structure = the 64-row pipelined chain of smz_net_bf16.cu (one CTA per 64-leaf tile runs the whole 2(L+2)-layer
 // chain on the SM; issuer warp + 16 epilogue warps; A operand and accumulators double-buffered; weights streamed by
 // cp.async.bulk two layers ahead; named-barrier hand-off of the A operand in two rounds of 96 + 32 columns), with
-// two A operands (hi, lo: 2 x 16 KB) and a weight ring of 2 x (hi, lo) x 32 KB.  One kernel serves the simulation
+// a 128-row stacked A operand (32 KB) and a weight ring of 2 x (hi, lo) x 32 KB.  One kernel serves the simulation
 // step (rows gathered through the descent's row records), the root step (observations) and stand-alone evaluation.
 // Hidden states live in the arena as [hi[64] fp16 | lo[64] fp16] = 256 B per row.
 #include <cuda_fp16.h>
