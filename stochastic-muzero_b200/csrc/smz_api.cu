@@ -190,7 +190,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   ALLOC(a.depth_sum, 1);
   a.xin_q = c.net_mode == SMZ_NET_TC32 ? 16 : 8;
   if (c.net_mode == SMZ_NET_BF16 || c.net_mode == SMZ_NET_TC32 || c.net_mode == SMZ_NET_F16) { ALLOC(a.xin, 2 * RC * a.xin_q); }
-  if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8); }
+  if (getenv("SMZ_TREE_TIMELINE")) { ALLOC(a.dbg, 8 + 4 * ((size_t)a.N + 2)); }
   ALLOC(a.out_policy, B * a.W); ALLOC(a.out_value, B); ALLOC(a.out_reward, B); ALLOC(a.dirichlet, B * a.A);
   if (c.record) {
     ALLOC(a.rec_policy, B * a.N * a.W); ALLOC(a.rec_value, B * a.N); ALLOC(a.rec_reward, B * a.N);
@@ -254,9 +254,24 @@ int smz_destroy(smz_engine* e) {
   DeviceGuard guard_(e->cfg.device);
   if (e->a.dbg) {
     long long t[8];
+    std::vector<unsigned long long> w(4 * ((size_t)e->a.N + 2));
+    if (cudaMemcpy(w.data(), e->a.dbg + 8, w.size() * sizeof(w[0]), cudaMemcpyDeviceToHost) == cudaSuccess && e->a.N >= 12) {
+      // wall clock (ns) of the last search, averaged over simulations N-11 .. N-2
+      double tree = 0, net = 0, g1 = 0, g2 = 0;
+      int n = 0;
+      for (int s = e->a.N - 11; s <= e->a.N - 2; ++s, ++n) {
+        const unsigned long long *c = &w[4 * s], *nx = &w[4 * (s + 1)];
+        net += (double)(c[3] - c[2]);            // network step of s: first wait-return -> last CTA end
+        g1 += (double)((long long)c[0] - (long long)c[3]);   // -> first wait-return of the tree step of s
+        tree += (double)(c[1] - c[0]);           // tree step of s (+ descent of s+1)
+        g2 += (double)((long long)nx[2] - (long long)c[1]);  // -> first wait-return of the network step of s+1
+      }
+      fprintf(stderr, "smz step timeline (%%globaltimer, mean of %d simulations): network step %.2f us | -> tree step %.2f us | tree step %.2f us | -> network step %.2f us\n",
+              n, net / n / 1e3, g1 / n / 1e3, tree / n / 1e3, g2 / n / 1e3);
+    }
     if (cudaMemcpy(t, e->a.dbg, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "smz tree timeline (block 0, last fused launch): expand+backup %lld cycles | descent %lld cycles (path length of tree 0: %lld)\n",
-              t[1] - t[0], t[2] - t[1], t[3]);
+      fprintf(stderr, "smz tree timeline (block 0, last fused launch): expand+backup %lld cycles | descent %lld cycles = %lld levels walked by warp 0 in %lld + leaf record / row reservation %lld (path length of tree 0: %lld)\n",
+              t[1] - t[0], t[2] - t[1], t[5], t[4] - t[1], t[2] - t[4], t[3]);
   }
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
@@ -368,6 +383,12 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   CU(cudaMemsetAsync(a.branch_count, 0, (size_t)(a.N + 1) * 2 * sizeof(int), s));
   CU(cudaMemsetAsync(a.error_flag, 0, sizeof(int), s));
   CU(cudaMemsetAsync(a.depth_sum, 0, sizeof(unsigned long long), s));
+  if (a.dbg) {      // wall-clock stamps: "first" slots start at all-ones (atomicMin), "last" slots at zero (atomicMax)
+    std::vector<unsigned long long> init(4 * ((size_t)a.N + 2));
+    for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+    CU(cudaMemcpyAsync(a.dbg + 8, init.data(), init.size() * sizeof(init[0]), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+  }
   e->launches = 0;
   if (e->cfg.num_simulations == 0) train = 0;   // mcts.py:215-216
   const float* policy = root_policy;

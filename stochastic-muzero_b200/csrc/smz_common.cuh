@@ -80,6 +80,19 @@ struct SmzArena {
 };
 
 #ifdef __CUDACC__
+// debug (SMZ_TREE_TIMELINE=1): wall-clock stamps per simulation in a.dbg[8 + 4 sim + k]: k = 0 / 2 first wait-return of
+// the tree / network step, k = 1 / 3 last block end of the tree / network step (atomicMin / atomicMax over the blocks)
+__device__ __forceinline__ unsigned long long smz_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void smz_stamp_min(long long* dbg, int sim, int k) {
+  if (dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(dbg) + 8 + 4 * sim + k, smz_globaltimer());
+}
+__device__ __forceinline__ void smz_stamp_max(long long* dbg, int sim, int k) {
+  if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(dbg) + 8 + 4 * sim + k, smz_globaltimer());
+}
 __device__ __forceinline__ size_t smz_row_index(const SmzArena& a, int sim, int branch, int row) {
   return (size_t)(sim & 1) * a.row_cap + (branch ? a.row_top - 1 - row : row);
 }

@@ -807,6 +807,7 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
   }
   smz_pdl_wait();
   smz_pdl_launch_dependents();
+  smz_stamp_min(a.dbg, sim, 2);
   if (tl && tid == 0) tl[1 + 4 * MAXL] = clock64();
   // gather: a staging thread owns the 16-byte K-chunk skc of leaf srow of the tile; requested before the counts are known
   const bool stager = HALF ? tid < 256 : !is_issuer_warp;
@@ -1157,6 +1158,7 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
   }
   tc_fence_before();
   __syncthreads();
+  smz_stamp_max(a.dbg, sim, 3);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TN) : "memory");
   }

@@ -165,6 +165,7 @@ __global__ void k_backup_select_sm(SmzArena a, int n_trees, int sim, int n_tab) 
   if (rng.mode == 0) { rng.win = swin; rng.win_base = cursor0; rng.win_len = SMZ_UWIN; }
   smz_pdl_wait();                 // the network step of `sim` must have landed
   smz_pdl_launch_dependents();    // the next network step may set itself up (barriers, TMEM, weights)
+  smz_stamp_min(a.dbg, sim, 0);
   __syncthreads();
   const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
   if (stamp) a.dbg[0] = clock64();
@@ -174,6 +175,8 @@ __global__ void k_backup_select_sm(SmzArena a, int n_trees, int sim, int n_tab) 
   if (stamp) a.dbg[1] = clock64();
   select_phase<G, true, true, true>(g, al, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr, sst, slk, srp);
   if (stamp) { a.dbg[2] = clock64(); a.dbg[3] = a.path_len[tree]; }
+  __syncthreads();
+  smz_stamp_max(a.dbg, sim, 1);
 }
 
 // ------------------------------------------------------------------------------------------------

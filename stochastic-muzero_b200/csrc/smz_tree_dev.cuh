@@ -62,10 +62,14 @@ __device__ float np_sum_f32(const Group<G>& g, float a, int n) {
   return n < 8 ? seq : res;
 }
 
-// cdf of RandomState.choice: float64 cumsum of p (sequential), divided by the last entry.
-// Every lane i < n returns cdf[i]; lanes >= n return 2.0 (never <= u).  Lanes >= n must pass p = 0.
+// cdf of RandomState.choice: float64 cumsum of p (sequential), divided by the last entry.  The DIVISION is what costs
+// (a float64 IEEE division is a ~40-instruction dependent chain) and its result is only ever COMPARED with a uniform
+// draw, so the phases keep every entry as numerator / total and decide `RN(num / total) <= u` in float32 whenever that
+// is safe: cf = num / total in float32 is within 3e-7 of the float64 quotient, so |cf - u| > 2e-6 settles the comparison;
+// a closer call (probability ~4e-6 per comparison) takes the exact division.
+// choice_cdf_raw: every lane i < n returns cumsum[i] (lanes >= n: 0) and `total` = cumsum[n-1] for the whole group.
 template <int G>
-__device__ double choice_cdf(const Group<G>& g, double p, int n) {
+__device__ double choice_cdf_raw(const Group<G>& g, double p, int n, double& total) {
   double acc = 0.0, mine = 0.0;
   if constexpr (G >= 16) {
     // Wide groups: inclusive scan by doubling (log2 G steps instead of G).  A sum of float32-born values is usually
@@ -86,8 +90,8 @@ __device__ double choice_cdf(const Group<G>& g, double p, int n) {
       }
     }
     if (!__any_sync(FULL, inexact)) {
-      acc = g.bcast(sc, G - 1);              // lanes >= n hold p = 0: the last lane carries the total
-      return (g.gl < n) ? __ddiv_rn(sc, acc) : 2.0;
+      total = g.bcast(sc, G - 1);            // lanes >= n hold p = 0: the last lane carries the total
+      return sc;
     }
   }
 #pragma unroll
@@ -95,23 +99,53 @@ __device__ double choice_cdf(const Group<G>& g, double p, int n) {
     acc = __dadd_rn(acc, g.bcast(p, i));     // + 0.0 beyond n leaves acc unchanged
     if (g.gl == i) mine = acc;
   }
-  return (g.gl < n) ? __ddiv_rn(mine, acc) : 2.0;
+  total = acc;
+  return mine;
+}
+constexpr float SMZ_CDF_MARGIN = 2e-6f;
+// this lane's cdf entry in float32 (lanes >= n: 3.0 — above every uniform and every "no draw" marker)
+__device__ __forceinline__ float cdf_f32(double num, double total, bool in_range) {
+  return in_range ? __fdividef((float)num, (float)total) : 3.f;
+}
+__device__ __forceinline__ double cdf_exact(double num, double total, bool in_range) {
+  return in_range ? __ddiv_rn(num, total) : 2.0;
 }
 
 // searchsorted(cdf, u, side='right') = #{i : cdf[i] <= u} for the non-decreasing cdf held one entry per lane
-// (lanes >= n hold 2.0); u may differ per lane.  The count never reaches G (cdf[n-1] = 1 > u, or 2.0 beyond n).
+// (num / total, lanes >= n never count); u may differ per lane.  The count never reaches G (cdf[n-1] = 1 > u).
 template <int G>
-__device__ int searchsorted_right(const Group<G>& g, double c, double u) {
+__device__ int searchsorted_right(const Group<G>& g, double num, double total, int n, double u) {
+  const float cf = cdf_f32(num, total, g.gl < n), uf = (float)u;
   int cnt = 0;
+  bool close = false;
   if constexpr (G >= 16) {
 #pragma unroll
     for (int step = G / 2; step >= 1; step >>= 1) {
-      const double cv = g.bcast(c, cnt + step - 1);
-      if (cv <= u) cnt += step;
+      const float cv = g.bcast(cf, cnt + step - 1);
+      close |= fabsf(cv - uf) <= SMZ_CDF_MARGIN;
+      if (cv < uf) cnt += step;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < G; ++i) cnt += g.bcast(c, i) <= u;
+    for (int i = 0; i < G; ++i) {
+      const float cv = g.bcast(cf, i);
+      close |= fabsf(cv - uf) <= SMZ_CDF_MARGIN;
+      cnt += cv < uf;
+    }
+  }
+  if (__any_sync(FULL, close)) {             // rare: some comparison of the warp is too close for float32
+    const double c = cdf_exact(num, total, g.gl < n);
+    cnt = 0;
+    if constexpr (G >= 16) {
+#pragma unroll
+      for (int step = G / 2; step >= 1; step >>= 1) {
+        const double cv = g.bcast(c, cnt + step - 1);
+        if (cv <= u) cnt += step;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < G; ++i) cnt += g.bcast(c, i) <= u;
+    }
   }
   return cnt;
 }
@@ -154,13 +188,14 @@ __device__ unsigned choice_without_replacement(const Group<G>& g, const SmzArena
       break;
     }
     const int m = bound - nf;                    // 0 for groups that are done; m <= bound <= n <= G
-    const double c = choice_cdf(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n);
+    double total;
+    const double num = choice_cdf_raw(g, ((found >> g.gl) & 1u) ? 0.0 : pd, n, total);
     const bool on = g.gl < m;
     double u = 2.0;                              // lanes without a draw never match
     if (__any_sync(FULL, on)) {
       if (on) u = smz_rng_uniform(rng, tree, cursor + g.gl);
     }
-    const int cnt = searchsorted_right(g, c, u);               // cdf of lanes >= n is 2.0: never <= u < 1
+    const int cnt = searchsorted_right(g, num, total, n, u);   // entries of lanes >= n never count
     const int idx = cnt < n ? cnt : n - 1;
     unsigned bits = on ? (1u << idx) : 0u;
 #pragma unroll
@@ -244,8 +279,15 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
       const float sh = act ? __fadd_rn(p, rem) : 0.f;
       const float tot = np_sum_f32(g, sh, nch);
       const float q = act ? __fdiv_rn(sh, tot) : 0.f;
-      const double c = choice_cdf(g, (double)q, nch);
-      int pk = __popc(g.ballot(act && c <= u));
+      double total;
+      const double num = choice_cdf_raw(g, (double)q, nch, total);
+      const float cf = cdf_f32(num, total, act), uf = (float)u;
+      bool le = cf < uf;
+      const bool close = act && fabsf(cf - uf) <= SMZ_CDF_MARGIN;
+      if (__any_sync(FULL, close)) {         // rare: float32 cannot decide RN(num / total) <= u
+        if (close) le = __ddiv_rn(num, total) <= u;
+      }
+      int pk = __popc(g.ballot(act && le));
       pk = pk < nch ? pk : nch - 1;
       if (chance) { pick = pk; cursor += going ? 1 : 0; }
     }
@@ -296,6 +338,7 @@ __device__ __forceinline__ void select_phase(const Group<G>& g, const SmzArena& 
     }
     ++level;
   }
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { a.dbg[4] = clock64(); a.dbg[5] = level; }
   // ---- leaf record.  The row compaction and the depth statistic are aggregated per warp: one atomic per branch
   //      (and one for the depth sum) per warp instead of one per tree — thousands of same-address atomics per
   //      simulation serialise in the L2 and their return value is on the critical path of the kernel.
