@@ -446,7 +446,7 @@ constexpr int NPIPE = NTHREADS + 32;      // + issuer warp
 struct SmemPipe {
   alignas(1024) unsigned char a[A_BYTES];
   alignas(1024) unsigned char w[2][W_BYTES];
-  float bias[MAXL][TN];
+  float bias[2][MAXL][TN];   // both chains: the branch of a tile is known only after the dependency wait
   unsigned long long wbar[2];
   unsigned long long dbar[2];
   unsigned long long bbar;
@@ -472,19 +472,17 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   const int r = (warp & 3) * 32 + lane;   // epilogue role: row of the tile == TMEM lane
   const int cb = (warp >> 2) & 3;         // head layers: 32-column block; hidden layers: 8-column slice of a round
 
-  int tile = blockIdx.x;
-  const int T = (job.n_rows + TM - 1) / TM;
-  const int branch = tile >= T;
-  tile -= branch * T;
-  const Chain& ch = branch ? chain1 : chain0;
-  const int nl = ch.n_layers;
+  // CTA i owns positions [i * 128, (i + 1) * 128) of the simulation's row array (smz_common.cuh): afterstate rows from the
+  // bottom, dynamics rows from the top, never both in one tile — no CTA is launched for an empty tile of the other branch
+  const int tile = blockIdx.x;
+  const int nl = chain0.n_layers;          // == chain1.n_layers
   long long* tl = (job.timeline && blockIdx.x == 0 && lane == 0) ? job.timeline : nullptr;   // debug stamps
   if (tl && tid == 0) tl[0] = clock64();
 
-  auto load_weights = [&](int l) {
-    const unsigned bytes = (unsigned)ch.layer[l].K * TN * 2;
-    mbar_expect_tx(&sm.wbar[l & 1], bytes);
-    bulk_g2s(sm.w[l & 1], ch.layer[l].w, bytes, &sm.wbar[l & 1]);
+  auto load_weights = [&](const Chain& c, int l, int slot) {
+    const unsigned bytes = (unsigned)c.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[slot], bytes);
+    bulk_g2s(sm.w[slot], c.layer[l].w, bytes, &sm.wbar[slot]);
   };
   if (tid == 0) {
     mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
@@ -492,10 +490,11 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     mbar_init(&sm.bbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const unsigned bbytes = (unsigned)nl * TN * 4;
-    mbar_expect_tx(&sm.bbar, bbytes);
-    bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
-    load_weights(0);
-    if (nl > 1) load_weights(1);
+    mbar_expect_tx(&sm.bbar, 2 * bbytes);
+    bulk_g2s(sm.bias[0], chain0.bias, bbytes, &sm.bbar);
+    bulk_g2s(sm.bias[1], chain1.bias, bbytes, &sm.bbar);
+    load_weights(chain0, 0, 0);              // the first weight tile of BOTH chains: the branch is not known yet
+    load_weights(chain1, 0, 1);
   }
   __syncwarp();
   if (warp == 0) {
@@ -507,12 +506,13 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   // only now may the tree kernel of this simulation start: its prologue mirrors the tree arena into shared memory,
   // which the PREVIOUS tree kernel (complete once the wait above returns) was still writing
   smz_pdl_launch_dependents();
-  // The row record and the parent's hidden row are requested before the row count of this branch is known (three
-  // dependent L2 round trips become two): rows beyond the count hold stale but in-range records (zeroed at create).
+  // The row record and the parent's hidden row are requested together with the branch counts (one L2 round trip):
+  // positions beyond the live rows hold stale but in-range records (zeroed at create).
   int4 rec = make_int4(0, 0, 0, 0);
   uint4 hrow[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  const int pos = tile * TM + r;
   if (!is_issuer_warp) {
-    const size_t ri = smz_row_index(a, sim, branch, min(tile * TM + r, a.B - 1));
+    const size_t ri = (size_t)(sim & 1) * a.row_cap + pos;
     rec = a.rows4[ri];
     if (a.xin) {
 #pragma unroll
@@ -525,12 +525,14 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       for (int q = 0; q < 2; ++q) hrow[q] = *reinterpret_cast<const uint4*>(src16 + (cb * 2 + q) * 8);
     }
   }
-  const int count = a.branch_count[sim * 2 + branch];
-  if (tile * TM >= count) {        // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
+  const int count0 = a.branch_count[sim * 2], count1 = a.branch_count[sim * 2 + 1];
+  const int top1 = a.row_top - count1;      // dynamics rows occupy [top1, row_top)
+  const int branch = tile * TM < count0 ? 0 : ((tile + 1) * TM > top1 ? 1 : -1);
+  if (branch < 0) {                // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
     if (tid == 0) {
       mbar_wait(&sm.bbar, 0);
       mbar_wait(&sm.wbar[0], 0);
-      if (nl > 1) mbar_wait(&sm.wbar[1], 0);
+      mbar_wait(&sm.wbar[1], 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -539,6 +541,7 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(2 * TN) : "memory");
     return;
   }
+  const Chain& ch = branch ? chain1 : chain0;
   // TMEM address + barrier inits become visible to everybody here
   tc_fence_before();
   __syncthreads();
@@ -548,10 +551,30 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   if (is_issuer_warp) {
     // =========================== issuer warp: weights ring + tcgen05.mma =======================================
     const unsigned long long ad = umma_desc(s32(sm.a), CHUNK_A, 128);
+    // weight ring: layer l lives in slot (l + branch) & 1 (layer 0 of chain b was prefetched into slot b); a tile that is
+    // already resident in its slot (the tied hidden layers) is not streamed again.  nfill / nseen = fills issued to /
+    // waited for on each slot.
+    unsigned nfill[2] = {1u, 1u}, nseen[2] = {0u, 0u};
+    const __nv_bfloat16* resident[2];
+    resident[branch] = ch.layer[0].w;
+    resident[branch ^ 1] = nullptr;
+    if (nl > 1) {                              // layer 1 replaces the unused chain's prefetched tile
+      const int s1 = branch ^ 1;
+      mbar_wait(&sm.wbar[s1], 0);
+      nseen[s1] = 1u;
+      if (lane == 0) load_weights(ch, 1, s1);
+      nfill[s1] = 2u;
+      resident[s1] = ch.layer[1].w;
+      __syncwarp();
+    }
     for (int l = 0; l < nl; ++l) {
       const int nk = ch.layer[l].K / 16;
-      mbar_wait(&sm.wbar[l & 1], (l >> 1) & 1);
-      const unsigned long long bd = umma_desc(s32(sm.w[l & 1]), CHUNK_W, 128);
+      const int slot = (l + branch) & 1;
+      if (nseen[slot] < nfill[slot]) {
+        mbar_wait(&sm.wbar[slot], nseen[slot] & 1u);
+        ++nseen[slot];
+      }
+      const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
       for (int c = 0; c < NR; ++c) {
         // the A columns of round c of this layer are in shared memory.  Every barrier is consumed for every layer
@@ -571,17 +594,19 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       if (lane == 0) umma_commit(&sm.dbar[l & 1]);
       if (tl) tl[1 + l * 4 + 1] = clock64();
       __syncwarp();
-      if (l + 2 < nl) {                           // ring slot l&1 is reusable once these MMAs have completed
-        mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);
-        if (lane == 0) load_weights(l + 2);
+      if (l + 2 < nl && (resident[slot] != ch.layer[l + 2].w || job.stream_all)) {
+        mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);   // the slot is reusable once these MMAs have completed
+        if (lane == 0) load_weights(ch, l + 2, slot);
+        ++nfill[slot];
+        resident[slot] = ch.layer[l + 2].w;
         __syncwarp();
       }
     }
   } else {
     // =========================== epilogue warps =================================================================
-    const int row = tile * TM + r;
-    const bool valid = row < count;
+    const bool valid = branch ? pos >= top1 : pos < count0;
     const int index = valid ? rec.x : -1;
+    const float (*cbias)[TN] = sm.bias[branch];
     {   // stage the first A operand: thread (r, cb) fills K-chunks 2cb, 2cb+1 (+ its share of the one-hot chunks)
       const int act = valid ? rec.z : -1;
 #pragma unroll
@@ -623,7 +648,7 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < NR; ++c) {
-          const float* bias = sm.bias[l] + c * RC + j0;
+          const float* bias = cbias[l] + c * RC + j0;
           float x[SL];
 #pragma unroll
           for (int i = 0; i < SL; ++i) x[i] = elu_fast(__uint_as_float(raw[c][i]) + bias[i]);
@@ -640,7 +665,7 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         // head layers are not pipelined: row-wise reductions need all columns.  Same code as k_bf16_chain,
         // warp (quarter, cb) owns the 32-column block cb of its rows; barriers among the epilogue warps only.
         const int c0 = cb * 32;
-        const float* bias = sm.bias[l] + c0;
+        const float* bias = cbias[l] + c0;
         uint4 pend[4];
         uint4* pend_dst = nullptr;
         float x[32];
@@ -1750,7 +1775,7 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
   }
   if (tree_mode == 0 && im->use_pipe) {
     auto* kp = im->pipe_rounds == 4 ? k_bf16_chain_pipe<4> : k_bf16_chain_pipe<2>;
-    smz_launch(kp, grid, dim3(NPIPE), sizeof(SmemPipe) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    smz_launch(kp, dim3(a.row_top / TM), dim3(NPIPE), sizeof(SmemPipe) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
     return;
   }
   auto* k = tree_mode == 2 ? k_bf16_chain<2> : (tree_mode == 1 ? k_bf16_chain<1> : k_bf16_chain<0>);
