@@ -335,15 +335,17 @@ bool smz_tree_mirror_fits(const SmzArena& a, int lanes) {
   return !off && mirror_bytes(a, lanes) <= 96 * 1024;
 }
 
-// The mirror kernel is the low-latency variant (one block of 128 threads per SM or two); with many blocks per SM the
-// arena-only kernel wins on occupancy (measured crossover on B200, cfg-2 shapes: ~16 k trees = 512 blocks).
+// The mirror kernel is the low-latency variant (one block of 128 threads per SM or two); with more blocks per SM the
+// arena-only kernel wins on occupancy (measured on B200, cfg-2 shapes, round 2: 8192 trees = 256 blocks 1.53 ms with the
+// mirror vs 1.78 ms without; 12288 trees = 384 blocks 2.07 vs 1.84 ms; 16384 trees 2.30 vs 1.85 ms).
 static bool mirror_pays(int blocks) {
   static int sms_of[64] = {0};      // per device: engines of one process may live on different GPUs
   int dev = 0;
   cudaGetDevice(&dev);
   int& sms = sms_of[dev & 63];
   if (!sms && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
-  return blocks <= 3 * sms;
+  static const int per_sm = getenv("SMZ_MIRROR_BLOCKS_PER_SM") ? atoi(getenv("SMZ_MIRROR_BLOCKS_PER_SM")) : 2;   // tuning switch
+  return blocks <= per_sm * sms;
 }
 
 void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s) {
