@@ -554,25 +554,22 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     // weight ring: layer l lives in slot (l + branch) & 1 (layer 0 of chain b was prefetched into slot b); a tile that is
     // already resident in its slot (the tied hidden layers) is not streamed again.  nfill / nseen = fills issued to /
     // waited for on each slot.
-    unsigned nfill[2] = {1u, 1u}, nseen[2] = {0u, 0u};
-    const __nv_bfloat16* resident[2];
-    resident[branch] = ch.layer[0].w;
-    resident[branch ^ 1] = nullptr;
+    unsigned nfill0 = 1u, nfill1 = 1u, nseen0 = 0u, nseen1 = 0u;        // per slot, kept in registers (no indexed arrays)
+    const __nv_bfloat16 *res0 = branch ? nullptr : ch.layer[0].w, *res1 = branch ? ch.layer[0].w : nullptr;
     if (nl > 1) {                              // layer 1 replaces the unused chain's prefetched tile
       const int s1 = branch ^ 1;
       mbar_wait(&sm.wbar[s1], 0);
-      nseen[s1] = 1u;
       if (lane == 0) load_weights(ch, 1, s1);
-      nfill[s1] = 2u;
-      resident[s1] = ch.layer[1].w;
+      if (s1) { nseen1 = 1u; nfill1 = 2u; res1 = ch.layer[1].w; } else { nseen0 = 1u; nfill0 = 2u; res0 = ch.layer[1].w; }
       __syncwarp();
     }
     for (int l = 0; l < nl; ++l) {
       const int nk = ch.layer[l].K / 16;
       const int slot = (l + branch) & 1;
-      if (nseen[slot] < nfill[slot]) {
-        mbar_wait(&sm.wbar[slot], nseen[slot] & 1u);
-        ++nseen[slot];
+      const unsigned seen = slot ? nseen1 : nseen0;
+      if (seen < (slot ? nfill1 : nfill0)) {
+        mbar_wait(&sm.wbar[slot], seen & 1u);
+        if (slot) ++nseen1; else ++nseen0;
       }
       const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
@@ -594,11 +591,10 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       if (lane == 0) umma_commit(&sm.dbar[l & 1]);
       if (tl) tl[1 + l * 4 + 1] = clock64();
       __syncwarp();
-      if (l + 2 < nl && (resident[slot] != ch.layer[l + 2].w || job.stream_all)) {
+      if (l + 2 < nl && ((slot ? res1 : res0) != ch.layer[l + 2].w || job.stream_all)) {
         mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);   // the slot is reusable once these MMAs have completed
         if (lane == 0) load_weights(ch, l + 2, slot);
-        ++nfill[slot];
-        resident[slot] = ch.layer[l + 2].w;
+        if (slot) { ++nfill1; res1 = ch.layer[l + 2].w; } else { ++nfill0; res0 = ch.layer[l + 2].w; }
         __syncwarp();
       }
     }
@@ -883,25 +879,22 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
     // that is already resident in its slot is not streamed again — 6 bulk copies per chain instead of 12.
     // nfill / nseen = fills issued to / waited for on each slot; slot `branch` holds layer 0 (fill 0, prefetched),
     // the other slot's fill 0 was the unused chain's layer 0 and is replaced by layer 1 as soon as it has landed.
-    unsigned nfill[2] = {1u, 1u}, nseen[2] = {0u, 0u};
-    const __nv_bfloat16* resident[2];
-    resident[branch] = ch.layer[0].w;
-    resident[branch ^ 1] = nullptr;
+    unsigned nfill0 = 1u, nfill1 = 1u, nseen0 = 0u, nseen1 = 0u;        // per slot, kept in registers (no indexed arrays)
+    const __nv_bfloat16 *res0 = branch ? nullptr : ch.layer[0].w, *res1 = branch ? ch.layer[0].w : nullptr;
     if (nl > 1) {
       const int s1 = branch ^ 1;
       mbar_wait(&sm.wbar[s1], 0);
-      nseen[s1] = 1u;
       if (lane == 0) load_weights(ch, 1, s1);
-      nfill[s1] = 2u;
-      resident[s1] = ch.layer[1].w;
+      if (s1) { nseen1 = 1u; nfill1 = 2u; res1 = ch.layer[1].w; } else { nseen0 = 1u; nfill0 = 2u; res0 = ch.layer[1].w; }
       __syncwarp();
     }
     for (int l = 0; l < nl; ++l) {
       const int nk = ch.layer[l].K / 16;
       const int slot = (l + branch) & 1;
-      if (nseen[slot] < nfill[slot]) {
-        mbar_wait(&sm.wbar[slot], nseen[slot] & 1u);
-        ++nseen[slot];
+      const unsigned seen = slot ? nseen1 : nseen0;
+      if (seen < (slot ? nfill1 : nfill0)) {
+        mbar_wait(&sm.wbar[slot], seen & 1u);
+        if (slot) ++nseen1; else ++nseen0;
       }
       const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
       const unsigned d = tmem + (unsigned)((l & 1) * TN);
@@ -923,11 +916,10 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
       if (lane == 0) umma_commit(&sm.dbar[l & 1]);
       if (tl) tl[1 + l * 4 + 1] = clock64();
       __syncwarp();
-      if (l + 2 < nl && (resident[slot] != ch.layer[l + 2].w || job.stream_all)) {
+      if (l + 2 < nl && ((slot ? res1 : res0) != ch.layer[l + 2].w || job.stream_all)) {
         mbar_wait(&sm.dbar[l & 1], (l >> 1) & 1);            // the slot is free once these MMAs have completed
         if (lane == 0) load_weights(ch, l + 2, slot);
-        ++nfill[slot];
-        resident[slot] = ch.layer[l + 2].w;
+        if (slot) { ++nfill1; res1 = ch.layer[l + 2].w; } else { ++nfill0; res0 = ch.layer[l + 2].w; }
         __syncwarp();
       }
     }
@@ -1001,15 +993,24 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
         tmem_wait_ld();
         const bool fine = tl && warp == 0 && l == 2;
         if (fine) tl[1 + 4 * MAXL + 2] = clock64();
+        // 32-leaf tiles: the arithmetic of both rounds first (8 values per thread), then stores + fence per round;
+        // 64-leaf tiles (16 values per thread): round by round, or the packed results spill
         unsigned pa[G0 + G1], pb[G0 + G1];
-#pragma unroll
-        for (int g = 0; g < G0 + G1; ++g) {
+        auto math = [&](int g) {
           const unsigned* rr = raw + 4 * g;
           pa[g] = pack_bf16(elu_fast(__uint_as_float(rr[0]) + bi[g].x), elu_fast(__uint_as_float(rr[1]) + bi[g].y));
           if constexpr (!HALF) pb[g] = pack_bf16(elu_fast(__uint_as_float(rr[2]) + bi[g].x), elu_fast(__uint_as_float(rr[3]) + bi[g].y));
+        };
+        if constexpr (HALF) {
+#pragma unroll
+          for (int g = 0; g < G0 + G1; ++g) math(g);
         }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          if constexpr (!HALF) {
+#pragma unroll
+            for (int g = 0; g < (c ? G1 : G0); ++g) math((c ? G0 : 0) + g);
+          }
 #pragma unroll
           for (int g = 0; g < (c ? G1 : G0); ++g) {
             const int col = (c ? R0 + cb * 8 * G1 : cb * 8 * G0) + g * 8 + cq;
@@ -1190,7 +1191,7 @@ __device__ __forceinline__ void chain_m64_body(const SmzArena& a, const Chain& c
 }
 
 template <int R0>
-__global__ void __launch_bounds__(NPIPE, 1)
+__global__ void __maxnreg__(80)      // see k_bf16_chain_m32: measured 1.33 vs 1.50 ms per search at 6144 trees (98 CTAs)
 k_bf16_chain_m64(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   chain_m64_body<R0, false>(a, chain0, chain1, job, sim);
 }
@@ -1611,8 +1612,9 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   // they run (PDL): both kernels ask for the largest shared-memory carve-out, otherwise an SM is configured for the first
   // of them alone and the other's blocks wait for it to drain (measured: 156 vs 176 M sims/s on cfg2).  NOT set on the
   // arena-only tree kernels of the large batches — they live on the L1 (cfg4: 534 -> 480 M sims/s with it).
-  for (const void* f : {(const void*)k_bf16_chain_m64<64>, (const void*)k_bf16_chain_m64<96>, (const void*)k_bf16_chain_m32})
-    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (!getenv("SMZ_NO_CARVEOUT"))
+    for (const void* f : {(const void*)k_bf16_chain_m64<64>, (const void*)k_bf16_chain_m64<96>, (const void*)k_bf16_chain_m32})
+      cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   im->pipe_rounds = getenv("SMZ_PIPE_ROUNDS") ? atoi(getenv("SMZ_PIPE_ROUNDS")) : 2;
   if (getenv("SMZ_BF16_TIMELINE")) {
     cudaMalloc(&im->timeline, (1 + 4 * MAXL + 32) * sizeof(long long));

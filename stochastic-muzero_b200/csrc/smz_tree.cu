@@ -175,8 +175,10 @@ __global__ void k_backup_select_sm(SmzArena a, int n_trees, int sim, int n_tab) 
   if (stamp) a.dbg[1] = clock64();
   select_phase<G, true, true, true>(g, al, rng, tree, alive, sim + 1, ts, nullptr, nullptr, nullptr, sst, slk, srp);
   if (stamp) { a.dbg[2] = clock64(); a.dbg[3] = a.path_len[tree]; }
-  __syncthreads();
-  smz_stamp_max(a.dbg, sim, 1);
+  if (a.dbg) {
+    __syncthreads();
+    smz_stamp_max(a.dbg, sim, 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,6 +355,7 @@ void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim
     const size_t smem = mirror_bytes(a, lanes);
     SMZ_DISPATCH_G(lanes, (cudaFuncSetAttribute((const void*)k_backup_select_sm<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem),
+                           getenv("SMZ_NO_CARVEOUT") ? cudaSuccess :
                            cudaFuncSetAttribute((const void*)k_backup_select_sm<G>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                 cudaSharedmemCarveoutMaxShared),
                            smz_launch(k_backup_select_sm<G>, dim3(grid_for<G>(n_trees, kThreads)), dim3(kThreads), smem, s, pdl,
