@@ -331,15 +331,14 @@ class Bench:
         model = PackedModel(self.blob.cpu().numpy(), self.shape)
         obs_host = self.obs.cpu().pin_memory()
         for _ in range(3):
-            r = mcts.run_batch(obs_host, model, train=True)
-            r.visit_counts.cpu(); r.root_values.cpu()
+            mcts.run_batch(obs_host, model, train=True).host()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            r = mcts.run_batch(obs_host, model, train=True)
-            v_host, rv_host = r.visit_counts.cpu(), r.root_values.cpu()
+            h = mcts.run_batch(obs_host, model, train=True).host()     # one D2H: visits, root values, error flag
+            v_host, rv_host = h["visit_counts"], h["root_values"]
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=self.dev)
@@ -350,9 +349,9 @@ class Bench:
         self.model = model
         return {"value": world * self.B * self.N * steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(obs_host.numel() * 4),
-                "d2h_bytes_per_step": int(v_host.numel() * 4 + rv_host.numel() * 4 + 4),
+                "d2h_bytes_per_step": int(v_host.size * 4 + rv_host.size * 4 + 4),
                 "ms_per_step": 1e3 * e2e_s / steps,
-                "api": "Monte_carlo_tree_search.run_batch(pinned host observations) -> visit counts + root values "
+                "api": "Monte_carlo_tree_search.run_batch(pinned host observations).host() -> visit counts + root values "
                        "(+ the search's error flag) on host"}
 
     def close(self):

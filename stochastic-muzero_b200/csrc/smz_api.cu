@@ -350,10 +350,9 @@ int smz_set_weights(smz_engine* e, const float* blob, uint64_t n_floats, int32_t
 int smz_set_seed(smz_engine* e, uint64_t seed, uint64_t tree_id_offset, void* stream) {
   if (!e) return fail(SMZ_E_INVALID_ARG, "smz_set_seed: null engine");
   ON_DEVICE(e);
-  // stream-ordered 16-byte update through a kernel-free path: the values are baked into the memcpy node
-  const unsigned long long st[2] = {seed, tree_id_offset};
-  CU(cudaMemcpyAsync(e->seed_dev, st, sizeof(st), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  CU(cudaStreamSynchronize((cudaStream_t)stream));   // `st` is a stack buffer
+  // stream-ordered update by a one-thread kernel: the values travel as launch arguments, nothing to synchronise on
+  smz_launch_set_seed(e->seed_dev, seed, tree_id_offset, (cudaStream_t)stream);
+  CU(cudaGetLastError());
   e->cfg.seed = seed;
   e->cfg.tree_id_offset = tree_id_offset;
   return SMZ_OK;

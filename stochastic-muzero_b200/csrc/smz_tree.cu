@@ -377,6 +377,16 @@ void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperatur
   k_select_actions<<<(n_trees + 127) / 128, 128, 0, s>>>(a, n_trees, temperature, u, actions, policy, stored);
 }
 
+__global__ void k_set_seed(unsigned long long* dst, unsigned long long seed, unsigned long long tree_id_offset) {
+  dst[0] = seed;
+  dst[1] = tree_id_offset;
+}
+// stream-ordered update of the device-resident Philox key: the values travel as kernel arguments (no host buffer
+// whose lifetime would need a synchronisation)
+void smz_launch_set_seed(unsigned long long* dst, unsigned long long seed, unsigned long long tree_id_offset, cudaStream_t s) {
+  k_set_seed<<<1, 1, 0, s>>>(dst, seed, tree_id_offset);
+}
+
 void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s) {
   k_dirichlet<<<(n_trees + 127) / 128, 128, 0, s>>>(a, n_trees);
 }

@@ -50,6 +50,11 @@ def player_tables(number_of_player: int, custom_loop: Optional[str], n_depth: in
     return sign, to_play
 
 
+class RootStats(dict):
+    """read_roots() result: the tensors by name; ``block`` = the device block that holds visits | root values | error."""
+    block = None
+
+
 class SearchEngine:
     """One engine = one arena of ``max_trees`` trees on one GPU, driven on one CUDA stream."""
 
@@ -107,6 +112,7 @@ class SearchEngine:
         self.n_trees = 0
         self.generation = 0       # bumped by every root(): views of an older search can tell that they are stale
         self._keep = {}           # tensors the engine holds raw pointers to
+        self._pinned = {}         # pinned host staging buffers by size (BatchedRoots.host)
         # sqrt(n) * pb_c(n) with numpy's sqrt/log, exactly as monte_carlo_tree_search.py:236-237 evaluates
         # `np.sqrt(parent.visit_count) * pb_c` on this host (the product is then multiplied by the prior)
         base, init = int(search["pb_c_base"]), float(search["pb_c_init"])
@@ -257,12 +263,25 @@ class SearchEngine:
         return out
 
     # ------------------------------------------------------------------------------------------
+    def pinned(self, n_int32: int):
+        """A pinned host staging buffer of n int32 (kept per size: read-outs of equal shape reuse it)."""
+        buf = self._pinned.get(n_int32)
+        if buf is None:
+            buf = torch.empty(n_int32, dtype=torch.int32).pin_memory()
+            self._pinned[n_int32] = buf
+        return buf
+
     def read_roots(self, out=None):
         n, A = self.n_trees, self.A
         if out is None:
-            out = {"visits": self._new(n, A, dtype=torch.int32), "root_values": self._new(n, dtype=torch.float32),
+            # visit counts, root values and the error flag share ONE device block: a consumer on the host fetches all
+            # three with a single copy (BatchedRoots.host)
+            blk = self._new(n * A + n + 1, dtype=torch.int32)
+            out = {"visits": blk[:n * A].view(n, A), "root_values": blk[n * A:n * A + n].view(torch.float32),
                    "priors": self._new(n, A, dtype=torch.float64), "rewards": self._new(n, A, dtype=torch.float32),
-                   "error": self._new(1, dtype=torch.int32)}
+                   "error": blk[n * A + n:]}
+            out = RootStats(out)
+            out.block = blk
         self._check(self.lib.smz_read_roots(self._h, self._ptr(out.get("visits")), self._ptr(out.get("root_values")),
                                             self._ptr(out.get("priors")), self._ptr(out.get("rewards")),
                                             self._ptr(out.get("error")), self._stream))

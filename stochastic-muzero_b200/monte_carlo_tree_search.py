@@ -163,6 +163,8 @@ class BatchedRoots:
         self.rewards = stats["rewards"]           # float32 [B, A]
         self.root_values = stats["root_values"]   # float32 [B]
         self.error = stats.get("error")           # int32 [1] device: the search's error flag (engine.raise_for_error)
+        self._block = getattr(stats, "block", None)   # visit counts | root values | error flag in one device block
+        self._host = None
 
     def __len__(self):
         return int(self.visit_counts.shape[0])
@@ -173,11 +175,28 @@ class BatchedRoots:
                                    "was reset); read roots[i] / select_actions() / hidden_state before searching again")
         return self._engine
 
+    def host(self):
+        """Visit counts int32 [B, A], root values float32 [B] and the error flag on the HOST: one device-to-host copy
+        into a pinned buffer and one synchronisation for all three (cached: the check of ``run_batch`` already paid it)."""
+        if self._host is None:
+            B, A = self.visit_counts.shape
+            if self._block is not None:
+                pin = self._engine.pinned(self._block.numel())
+                pin.copy_(self._block, non_blocking=True)
+                torch.cuda.current_stream(self._block.device).synchronize()
+                buf = pin.numpy().copy()
+                self._host = {"visit_counts": buf[:B * A].reshape(B, A), "root_values": buf[B * A:B * A + B].view(np.float32),
+                              "error": int(buf[B * A + B])}
+            else:
+                self._host = {"visit_counts": self.visit_counts.cpu().numpy(), "root_values": self.root_values.cpu().numpy(),
+                              "error": int(self.error.item()) if self.error is not None else 0}
+        return self._host
+
     def raise_if_failed(self):
         """Synchronises on the read-out and raises what the reference would have raised inside ``run``
         (np.random.choice's ValueError on a NaN / all-zero policy, monte_carlo_tree_search.py:208/:294)."""
         if self.error is not None:
-            self._engine.raise_for_error(int(self.error.item()))
+            self._engine.raise_for_error(self.host()["error"])
         return self
 
     def select_actions(self, temperature: float = 0.0, uniforms=None):
