@@ -13,7 +13,6 @@ KEYS = [
     ("dyn smem/block B", "launch__shared_mem_per_block_dynamic"),
     ("SM busy % (sm__throughput)", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("tensor pipe active % of elapsed", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
-    ("tensor (hmma) cycles active, avg per SM", "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"),
     ("SM cycles active avg", "sm__cycles_active.avg"),
     ("XU (MUFU) pipe % of elapsed", "sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed"),
     ("FMA pipe %", "sm__inst_executed_pipe_fma_realtime.avg.pct_of_peak_sustained_elapsed"),
