@@ -494,7 +494,7 @@ def main():
     single = None
     if rank == 0 and world == 1 and not vision:
         from stochastic_muzero_b200 import Monte_carlo_tree_search
-        one = Monte_carlo_tree_search(**main_b.search, net="fp32", device=local, seed=5)
+        one = Monte_carlo_tree_search(**main_b.search, device=local, seed=5)       # default mode: reference precision (tc32)
         for _ in range(3):
             one.run(observation=torch.randn(1, shape.obs_dim), model=main_b.model, train=True)
         torch.cuda.synchronize()
@@ -505,7 +505,7 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         single = {"ms_per_move": 1e3 * dt / moves, "value": moves * N / dt, "unit": UNIT,
-                  "api": "Monte_carlo_tree_search.run(observation, model, train) -> Node, fp32 network step, 1 tree"}
+                  "api": "Monte_carlo_tree_search.run(observation, model, train) -> Node, default (fp32-grade tcgen05) network step, 1 tree"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline

@@ -238,9 +238,11 @@ class Monte_carlo_tree_search():
                  maxium_action_sample=2,
                  number_of_player=1,
                  custom_loop=None,
-                 *, net="fp32", device=None, seed=None, max_batch=None, tree_id_offset=None):
-        """Same nine arguments as the reference (:76-85).  Keyword-only extras: ``net`` ("fp32" exact
-        mode or "bf16" tensor-core mode for the fused MLP step), ``device`` (CUDA ordinal), ``seed``
+                 *, net="tc32", device=None, seed=None, max_batch=None, tree_id_offset=None):
+        """Same nine arguments as the reference (:76-85).  Keyword-only extras: ``net`` — the fused MLP network step:
+        "tc32" (default: the reference's fp32 precision on the tensor cores, fp16 hi/lo split operands, 1e-5 against the
+        reference's inference), "fp32" (the same precision on CUDA cores), "bf16" / "f16" (throughput modes with
+        stated tolerances); ``device`` (CUDA ordinal), ``seed``
         (Philox key; default drawn from numpy's global RNG so ``np.random.seed`` reproduces runs),
         ``max_batch`` (arena capacity reserved for ``run_batch``), ``tree_id_offset`` (global id of local tree 0:
         the Philox streams are keyed by (seed, global tree id), so ranks of a sharded self-play that seed
