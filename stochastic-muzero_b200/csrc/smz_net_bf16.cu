@@ -741,6 +741,306 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two tiles per CTA for batches of more than one wave (k_bf16_chain_pipe2).  With one 128-leaf tile per SM the tensor
+// pipe idles while the 16 epilogue warps work through a layer (~1800 cycles, MUFU / issue bound) and the epilogue warps
+// idle while the layer's last K-steps complete (~600 cycles).  A CTA that owns TWO adjacent tiles of the row array (256
+// positions: never both branches, see smz_common.cuh) alternates them: the epilogue warps do (tile 0, layer l), (tile 1,
+// layer l), (tile 0, layer l + 1) ... and the issuer feeds tile 0's layer l + 1 while tile 1's layer l is in the
+// epilogue — the contraction disappears behind the activation function.  Both tiles read the SAME weight tile
+// (one ring, one stream of bulk copies per pair); accumulators: 4 x 128 TMEM columns (tile x parity).
+// ---------------------------------------------------------------------------------------------
+struct SmemPipe2 {
+  alignas(1024) unsigned char a[2][A_BYTES];
+  alignas(1024) unsigned char w[2][W_BYTES];
+  float bias[2][MAXL][TN];
+  unsigned long long wbar[2];
+  unsigned long long dbar[2][2];   // [tile][accumulator parity]
+  unsigned long long bbar;
+  unsigned int tmem_base;
+  float4 part[2][4][TM];           // per tile: the head layers of the two tiles follow each other without a barrier between
+};
+
+__global__ void __launch_bounds__(NPIPE, 1)
+k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+  extern __shared__ unsigned char smem_raw[];
+  SmemPipe2& sm = *reinterpret_cast<SmemPipe2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NR = 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer_warp = warp == NEPI / 32;
+  const int r = (warp & 3) * 32 + lane;   // epilogue role: row of a tile == TMEM lane
+  const int cb = (warp >> 2) & 3;         // head layers: 32-column block; hidden layers: 16-column slice of a round
+  const int pair = blockIdx.x;            // positions [256 pair, 256 pair + 256) of the row array
+  const int nl = chain0.n_layers;
+
+  auto load_weights = [&](const Chain& c, int l, int slot) {
+    const unsigned bytes = (unsigned)c.layer[l].K * TN * 2;
+    mbar_expect_tx(&sm.wbar[slot], bytes);
+    bulk_g2s(sm.w[slot], c.layer[l].w, bytes, &sm.wbar[slot]);
+  };
+  if (tid == 0) {
+    mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
+    mbar_init(&sm.dbar[0][0], 1); mbar_init(&sm.dbar[0][1], 1);
+    mbar_init(&sm.dbar[1][0], 1); mbar_init(&sm.dbar[1][1], 1);
+    mbar_init(&sm.bbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bbytes = (unsigned)nl * TN * 4;
+    mbar_expect_tx(&sm.bbar, 2 * bbytes);
+    bulk_g2s(sm.bias[0], chain0.bias, bbytes, &sm.bbar);
+    bulk_g2s(sm.bias[1], chain1.bias, bbytes, &sm.bbar);
+    load_weights(chain0, 0, 0);              // the first weight tile of BOTH chains: the branch is not known yet
+    load_weights(chain1, 0, 1);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(4 * TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  smz_pdl_wait();
+  smz_pdl_launch_dependents();
+  // row records + parent hidden rows of both tiles, requested together with the branch counts
+  int4 rec[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+  uint4 hrow[2][2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) hrow[t][0] = hrow[t][1] = make_uint4(0, 0, 0, 0);
+  if (!is_issuer_warp) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const size_t ri = (size_t)(sim & 1) * a.row_cap + (size_t)(2 * pair + t) * TM + r;
+      rec[t] = a.rows4[ri];
+      if (a.xin) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) hrow[t][q] = a.xin[ri * 8 + cb * 2 + q];
+      } else {
+        rec[t].x = min(max(rec[t].x, 0), a.B - 1);
+        rec[t].y = min(max(rec[t].y, 0), a.N);
+        const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(a.hidden) + ((size_t)rec[t].y * a.B + rec[t].x) * SMZ_SP;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) hrow[t][q] = *reinterpret_cast<const uint4*>(src16 + (cb * 2 + q) * 8);
+      }
+    }
+  }
+  const int count0 = a.branch_count[sim * 2], count1 = a.branch_count[sim * 2 + 1];
+  const int top1 = a.row_top - count1;      // dynamics rows occupy [top1, row_top)
+  const int lo = 2 * pair * TM;
+  const int branch = lo < count0 ? 0 : (lo + 2 * TM > top1 ? 1 : -1);
+  if (branch < 0) {                // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
+    if (tid == 0) {
+      mbar_wait(&sm.bbar, 0);
+      mbar_wait(&sm.wbar[0], 0);
+      mbar_wait(&sm.wbar[1], 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(4 * TN) : "memory");
+    return;
+  }
+  // which of the two tiles carries rows (CTA-uniform): afterstate rows fill the pair from below, dynamics rows from above
+  const bool act0 = branch ? lo + TM > top1 : true;
+  const bool act1 = branch ? true : lo + TM < count0;
+  const Chain& ch = branch ? chain1 : chain0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = sm.tmem_base;
+
+  if (is_issuer_warp) {
+    // =========================== issuer warp: one weight ring, two tiles ======================================
+    unsigned nfill0 = 1u, nfill1 = 1u, nseen0 = 0u, nseen1 = 0u;
+    const __nv_bfloat16 *res0 = branch ? nullptr : ch.layer[0].w, *res1 = branch ? ch.layer[0].w : nullptr;
+    if (nl > 1) {                              // layer 1 replaces the unused chain's prefetched tile
+      const int s1 = branch ^ 1;
+      mbar_wait(&sm.wbar[s1], 0);
+      if (lane == 0) load_weights(ch, 1, s1);
+      if (s1) { nseen1 = 1u; nfill1 = 2u; res1 = ch.layer[1].w; } else { nseen0 = 1u; nfill0 = 2u; res0 = ch.layer[1].w; }
+      __syncwarp();
+    }
+    for (int l = 0; l < nl; ++l) {
+      const int nk = ch.layer[l].K / 16;
+      const int slot = (l + branch) & 1;
+      const unsigned seen = slot ? nseen1 : nseen0;
+      if (seen < (slot ? nfill1 : nfill0)) {
+        mbar_wait(&sm.wbar[slot], seen & 1u);
+        if (slot) ++nseen1; else ++nseen0;
+      }
+      const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (!(t ? act1 : act0)) continue;
+        const unsigned long long ad = umma_desc(s32(sm.a[t]), CHUNK_A, 128);
+        const unsigned d = tmem + (unsigned)((2 * t + (l & 1)) * TN);
+        for (int c = 0; c < NR; ++c) {
+          nb_sync(2 + 2 * t + c);               // the A columns of round c of tile t are in shared memory
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k >= 4 * c && k < 4 * (c + 1) && k < nk)
+                umma(d, ad + (unsigned long long)(k * ((2 * CHUNK_A) >> 4)), bd + (unsigned long long)(k * ((2 * CHUNK_W) >> 4)),
+                     k > 0 ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) umma_commit(&sm.dbar[t][l & 1]);
+        __syncwarp();
+      }
+      if (l + 2 < nl && ((slot ? res1 : res0) != ch.layer[l + 2].w || job.stream_all)) {
+        // the slot is reusable once the MMAs of BOTH tiles have completed (commits complete in issue order)
+        mbar_wait(&sm.dbar[act1 ? 1 : 0][l & 1], (l >> 1) & 1);
+        if (lane == 0) load_weights(ch, l + 2, slot);
+        if (slot) { ++nfill1; res1 = ch.layer[l + 2].w; } else { ++nfill0; res0 = ch.layer[l + 2].w; }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== epilogue warps: (tile 0, l), (tile 1, l), (tile 0, l + 1), ... =====================
+    int index[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int pos = lo + t * TM + r;
+      const bool valid = (t ? act1 : act0) && (branch ? pos >= top1 : pos < count0);
+      index[t] = valid ? rec[t].x : -1;
+      if (t ? act1 : act0) {   // stage the first A operand of tile t
+        const int act = valid ? rec[t].z : -1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) a_store(sm.a[t], r, cb * 2 + q, valid ? hrow[t][q] : make_uint4(0, 0, 0, 0));
+        for (int kc = cb; kc < ch.onehot_pad / 8; kc += 4) {
+          unsigned w4[4] = {0, 0, 0, 0};
+          if (valid && act >= kc * 8 && act < kc * 8 + 8) {
+            const int j = act - kc * 8;
+            w4[j >> 1] = (j & 1) ? 0x3F800000u : 0x00003F80u;
+          }
+          a_store(sm.a[t], r, 8 + kc, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+        }
+      }
+    }
+    fence_async_smem();
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (t ? act1 : act0)
+        for (int c = 0; c < NR; ++c) nb_arrive(2 + 2 * t + c);
+    mbar_wait(&sm.bbar, 0);
+    const float (*cbias)[TN] = sm.bias[branch];
+    const int S = job.S;
+
+    for (int l = 0; l < nl; ++l) {
+      const int kind = ch.layer[l].kind;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (!(t ? act1 : act0)) continue;
+        unsigned char* const A = sm.a[t];
+        const unsigned lane_t = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((2 * t + (l & 1)) * TN);
+        mbar_wait(&sm.dbar[t][l & 1], (l >> 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+        if (kind == LK_HIDDEN) {
+          constexpr int SL = 32 / NR;              // 16-column slice of every round
+          constexpr int RC = TN / NR;              // 64 columns per round
+          const int j0 = cb * SL;
+          unsigned raw[NR][SL];
+#pragma unroll
+          for (int c = 0; c < NR; ++c) tmem_ld16_nowait(lane_t + c * RC + j0, raw[c]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < NR; ++c) {
+            const float* bias = cbias[l] + c * RC + j0;
+            float x[SL];
+#pragma unroll
+            for (int i = 0; i < SL; ++i) x[i] = elu_fast(__uint_as_float(raw[c][i]) + bias[i]);
+#pragma unroll
+            for (int q = 0; q < SL / 8; ++q)
+              a_store(A, r, (c * RC + j0) / 8 + q,
+                      make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                 pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7])));
+            fence_async_smem();
+            if (c == NR - 1) tc_fence_before();
+            nb_arrive(2 + 2 * t + c);
+          }
+        } else {
+          // head layers: row-wise reductions need all columns; warp (quarter, cb) owns the 32-column block cb of its rows
+          const int c0 = cb * 32;
+          const float* bias = cbias[l] + c0;
+          float4 (*part)[TM] = sm.part[t];
+          uint4 pend[4];
+          uint4* pend_dst = nullptr;
+          float x[32];
+          tmem_ld32(lane_t + c0, x);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] += bias[i];
+          const bool state_seg = (kind == LK_STATE || kind == LK_STATE_REWARD) && cb < 2;
+          const bool soft_seg = (kind == LK_STATE_REWARD && cb >= 2) || (kind == LK_PRED && cb < 2);
+          SoftPart sp{-1e30f, 0.f, 0.f};
+          if (state_seg) {
+            float lo_ = INFINITY, hi_ = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { lo_ = fminf(lo_, x[i]); hi_ = fmaxf(hi_, x[i]); }
+            part[cb][r] = make_float4(lo_, hi_, 0.f, 0.f);
+          } else if (soft_seg) {
+            sp = soft_part(x, c0 & 63, S);
+            part[cb][r] = make_float4(sp.m, sp.z, sp.y, 0.f);
+          }
+          epi_sync();
+          if (state_seg) {
+            const float4 o = part[cb ^ 1][r];
+            const float lo_ = fminf(part[cb][r].x, o.x), hi_ = fmaxf(part[cb][r].y, o.y);
+            float scale = hi_ - lo_;
+            if (scale < 1e-5f) scale += 1e-5f;
+            const float inv = 1.f / scale;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = (x[i] - lo_) * inv;
+            if (index[t] >= 0 && job.hidden16_dst) pend_dst = reinterpret_cast<uint4*>(job.hidden16_dst + (size_t)index[t] * SMZ_SP + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              pend[q] = make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                   pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+              a_store(A, r, cb * 4 + q, pend[q]);
+            }
+          } else if (soft_seg && (cb & 1) == 0) {
+            const float4 o = part[cb + 1][r];
+            const float v = support_scalar(sp, SoftPart{o.x, o.y, o.z});
+            float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
+            if (index[t] >= 0 && dst) dst[index[t]] = v;
+          } else if (kind == LK_PRED && cb == 2) {
+            const int n = ch.n_policy;
+            float m = -1e30f, z = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, x[i]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              x[i] = ex2f((x[i] - m) * 1.4426950408889634f);
+              z += x[i];
+            }
+            if (index[t] >= 0 && job.policy_dst) {
+              float* dst = job.policy_dst + (size_t)index[t] * job.pstride;
+              const float inv = 1.f / z;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < n) dst[i] = x[i] * inv;
+            }
+          }
+          if (l + 1 < nl) {
+            fence_async_smem();
+            tc_fence_before();
+            for (int c = 0; c < NR; ++c) nb_arrive(2 + 2 * t + c);
+          }
+          if (pend_dst) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pend_dst[q] = pend[q];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(4 * TN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 64-row tiles (chosen automatically for small batches, SMZ_M64=0/1 forces): the hidden-layer epilogue is bound by the MUFU pipe of the SM (128 x 128
 // exponentials per layer at 16 per clock), so a tile of 64 leaves per CTA on twice as many SMs halves it.
 // tcgen05.mma M = 64 puts accumulator row m in TMEM lane (m % 16) + 32 * (m / 16): every warp quarter owns 16 rows,
@@ -1551,6 +1851,7 @@ struct SmzBf16Image {
   int n_sms;
   int timeline_mega;
   int use_pipe;           // K-pipelined chain for the simulation step (SMZ_NO_PIPE=1 turns it off)
+  int use_pipe2;          // two 128-leaf tiles per CTA: -1 = when the tiles exceed one wave of SMs, SMZ_PIPE2=0/1 forces
 };
 
 static int round16(int v) { return (v + 15) / 16 * 16; }
@@ -1598,6 +1899,8 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   im->use_pipe = getenv("SMZ_NO_PIPE") ? 0 : 1;
+  cudaFuncSetAttribute((const void*)k_bf16_chain_pipe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe2) + 1024);
+  im->use_pipe2 = getenv("SMZ_PIPE2") ? atoi(getenv("SMZ_PIPE2")) : -1;
   im->use_m64 = getenv("SMZ_M64") ? atoi(getenv("SMZ_M64")) : -1;
   {
     int dev = 0;
@@ -1772,6 +2075,12 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
     const bool uneven = getenv("SMZ_M64_EVEN") == nullptr;     // 96 + 32 columns measured 2.7 % faster than 64 + 64
     auto* k64 = m32 ? k_bf16_chain_m32 : (uneven ? k_bf16_chain_m64<96> : k_bf16_chain_m64<64>);
     smz_launch(k64, dim3(a.row_top / (m32 ? 32 : TM64)), dim3(NPIPE), sizeof(Smem64) + 1024, s, pdl, a, im->chain_after,
+               im->chain_dyn, job, sim);
+    return;
+  }
+  const bool pipe2 = (im->use_pipe2 < 0 ? a.row_top / TM > im->n_sms : im->use_pipe2 != 0) && a.row_top % (2 * TM) == 0;
+  if (tree_mode == 0 && im->use_pipe && pipe2) {
+    smz_launch(k_bf16_chain_pipe2, dim3(a.row_top / (2 * TM)), dim3(NPIPE), sizeof(SmemPipe2) + 1024, s, pdl, a, im->chain_after,
                im->chain_dyn, job, sim);
     return;
   }
