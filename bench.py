@@ -42,7 +42,7 @@ WORKLOADS = {
 }
 KERNEL_NAMES = {"bf16": "k_bf16_chain_m32 / _m64 / _pipe / _pipe2 by batch size, tcgen05 kind::f16 on bf16 operands",
                 "f16": "k_tc32_chain_m64<1>, tcgen05 kind::f16 on fp16 operands (one product)",
-                "tc32": "k_tc32_chain_m64, tcgen05 kind::f16 on fp16 hi/lo split operands (3 products, fp32-grade)",
+                "tc32": "k_tc32_chain_m64, tcgen05 kind::f16 on fp16 hi/lo split operands (hi and lo rows stacked along M: 2 MMAs per K-step give all 4 partial products, fp32-grade)",
                 "fp32": "k_net_sim, fp32 CUDA cores", "vision": "k_vision_step, fp32 CUDA cores"}
 DTYPES = {"bf16": "bf16", "f16": "f16", "tc32": "f32 (fp16 hi+lo split operands, fp32 accumulate)", "fp32": "f32", "vision": "f32"}
 
