@@ -435,7 +435,7 @@ int smz_select(smz_engine* e, int32_t sim, int32_t* slot, int32_t* action, int32
 
 // returns the number of kernels launched
 static int enqueue_net(smz_engine* e, int sim, cudaStream_t s, bool pdl = false, int tree_mode = 0) {
-  if (e->vision) return smz_vision_sim(e->vision, e->a, e->n_trees, sim, s);
+  if (e->vision) return smz_vision_sim(e->vision, e->a, e->n_trees, sim, pdl, s);
   if (e->bf16) smz_bf16_sim(e->bf16, e->a, e->shape, e->n_trees, sim, pdl, tree_mode, s);
   else if (e->tc32) smz_tc32_sim(e->tc32, e->a, e->shape, e->n_trees, sim, pdl, s);
   else smz_net_f32_sim(e->a, e->shape, e->img32, e->n_trees, sim, s);
@@ -488,7 +488,7 @@ static int enqueue_sims(smz_engine* e, int first, int n_sims, cudaStream_t s) {
   // select(first); then per simulation: network step, then [expand+backup(sim) fused with select(sim+1)]
   // With the tensor-core network both hot kernels are chained by programmatic dependent launch: the
   // next kernel's CTAs become resident and run their prologue while the previous one drains.
-  const bool pdl = (e->bf16 != nullptr || e->tc32 != nullptr) && e->use_pdl;
+  const bool pdl = (e->bf16 != nullptr || e->tc32 != nullptr || smz_vision_has_tc(e->vision)) && e->use_pdl;
   smz_launch_select(a, G, e->n_trees, first, nullptr, nullptr, nullptr, s);
   int launched = 1;
   // tensor-core network + 4 lanes per tree: the tree phases run in the tail of the network kernel (one launch
@@ -535,7 +535,7 @@ int smz_simulate(smz_engine* e, int32_t n_sims, void* stream) {
       ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
       cudaGraphDestroy(graph);
     }
-    if (ce != cudaSuccess && e->use_pdl && (e->bf16 || e->tc32)) {
+    if (ce != cudaSuccess && e->use_pdl && (e->bf16 || e->tc32 || e->vision)) {
       // programmatic edges not capturable on this driver: fall back to plain stream order, once
       cudaGetLastError();
       e->graph_exec = nullptr;

@@ -1080,12 +1080,13 @@ int smz_tc32_vision_pack(SmzTc32VisionHeads* im, const float* blob, const SmzVis
 }
 
 // heads of simulation `sim` for the compacted rows of both branches; feat as written by the convolution stage
-void smz_tc32_vision_heads(SmzTc32VisionHeads* im, const SmzArena& a, int n_trees, int sim, const float* feat, cudaStream_t s) {
+void smz_tc32_vision_heads(SmzTc32VisionHeads* im, const SmzArena& a, int n_trees, int sim, const float* feat, bool pdl,
+                           cudaStream_t s) {
   Job job{};
   job.input_kind = IN_FEAT; job.n_rows = n_trees; job.S = im->S;
   job.feat = feat; job.vchains = im->chains_dev;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   Chain none{};
-  smz_launch(k_tc32_chain_m64<3, false, true, KVIS>, dim3(5 * ((n_trees + TM - 1) / TM)), dim3(NTHR), (size_t)im->smem_bytes, s, false,
+  smz_launch(k_tc32_chain_m64<3, false, true, KVIS>, dim3(5 * ((n_trees + TM - 1) / TM)), dim3(NTHR), (size_t)im->smem_bytes, s, pdl,
              a, none, none, job, sim);
 }

@@ -33,4 +33,4 @@ void smz_tc32_vision_destroy(SmzTc32VisionHeads* im);
 int smz_tc32_vision_pack(SmzTc32VisionHeads* im, const float* blob_dev, const SmzVisionHeadSrc* src, cudaStream_t s, char* err,
                          size_t err_len);
 // feat: [3 heads: reward, value, policy][2 branches][a.B rows][160] fp32, rows in the compacted order of the simulation
-void smz_tc32_vision_heads(SmzTc32VisionHeads* im, const SmzArena& a, int n_trees, int sim, const float* feat, cudaStream_t s);
+void smz_tc32_vision_heads(SmzTc32VisionHeads* im, const SmzArena& a, int n_trees, int sim, const float* feat, bool pdl, cudaStream_t s);

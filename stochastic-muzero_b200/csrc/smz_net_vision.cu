@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(FEAT ? NTC : NT) k_vision_step(SmzArena a, VNe
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemSim<R>& sm = *reinterpret_cast<SmemSim<R>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  smz_pdl_wait();                 // no-op unless launched with a programmatic dependency (simulation step)
+  smz_pdl_launch_dependents();
   // Three CTAs share a tile of 32 leaves, one per MLP head (the heads are ~80 % of the work and independent):
   // head 0 = reward (dynamics pair only), 1 = value (also writes the new hidden state), 2 = policy.  The cheap
   // convolution trunk is recomputed by each.
@@ -686,16 +688,20 @@ void smz_vision_root(SmzVisionImage* im, const SmzArena& a, int n_trees, const f
   k_vision_step<false, R><<<3 * ((n_trees + R - 1) / R), NT, sizeof(SmemSim<R>), s>>>(a, im->nets, job, 0);
 }
 
+bool smz_vision_has_tc(const SmzVisionImage* im) { return im != nullptr && im->tc != nullptr; }
+
 // returns the number of kernels launched
-int smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, cudaStream_t s) {
+int smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, bool pdl, cudaStream_t s) {
   VJob job{};
   job.mode = 0; job.n_rows = n_trees;
   job.hidden_dst = a.hidden + (size_t)(sim + 1) * a.B * VSP;
   job.policy_dst = a.out_policy; job.value_dst = a.out_value; job.reward_dst = a.out_reward; job.pstride = a.W;
   if (im->tc && n_trees <= im->max_trees) {
     job.feat = im->feat;
-    k_vision_step<true, RC><<<(n_trees + RC - 1) / RC + 1, NTC, sizeof(SmemSim<RC>), s>>>(a, im->nets, job, sim);
-    smz_tc32_vision_heads(im->tc, a, n_trees, sim, im->feat, s);
+    // convolution stage -> head chains -> tree step are chained by programmatic dependent launch like the MLP family's
+    // two kernels: each one's prologue (weight tiles, tree mirror) runs while its predecessor drains
+    smz_launch(k_vision_step<true, RC>, dim3((n_trees + RC - 1) / RC + 1), dim3(NTC), sizeof(SmemSim<RC>), s, pdl, a, im->nets, job, sim);
+    smz_tc32_vision_heads(im->tc, a, n_trees, sim, im->feat, pdl, s);
     return 2;
   }
   k_vision_step<false, R><<<3 * ((n_trees + R - 1) / R + 1), NT, sizeof(SmemSim<R>), s>>>(a, im->nets, job, sim);

@@ -17,7 +17,8 @@ int smz_vision_pack(SmzVisionImage* im, const float* blob_dev, cudaStream_t s, c
 void smz_vision_root(SmzVisionImage* im, const SmzArena& a, int n_trees, const float* obs, cudaStream_t s);
 // one simulation's network step; returns the number of kernels launched (convolution stage + tensor-core heads, or the
 // single all-CUDA-core kernel with SMZ_VISION_CC=1)
-int smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, cudaStream_t s);
+bool smz_vision_has_tc(const SmzVisionImage* im);      // the head chains run on the tensor cores (PDL-chained step)
+int smz_vision_sim(SmzVisionImage* im, const SmzArena& a, int n_trees, int sim, bool pdl, cudaStream_t s);
 // which: 0 repr(obs) 1 pred 2 adyn 3 apred 4 dyn; hidden rows are float[n][SMZ_VISION_SP]
 int smz_vision_eval(SmzVisionImage* im, int which, int n_rows, const float* in, const int* idx, float* hidden_out,
                     float* policy_out, float* value_out, float* reward_out, int policy_stride, cudaStream_t s);
