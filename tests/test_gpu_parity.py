@@ -949,6 +949,26 @@ def test_views_of_an_older_search_are_refused():
     assert sum(c.visit_count for c in root1.children.values()) == 10      # materialised statistics survive
 
 
+def test_host_readout_is_one_consistent_copy():
+    """BatchedRoots.host(): visit counts, root values and the error flag fetched with one copy equal the device tensors,
+    and stay what they were after the arena has been reused by a later search."""
+    from fake_muzero import FakeMuzero
+    from stochastic_muzero_b200 import Monte_carlo_tree_search
+    zn = golden_io.load_net_case("mlp450_seed0")
+    model = FakeMuzero(zn["weights"], *[int(v) for v in zn["dims"]])
+    mcts = Monte_carlo_tree_search(discount=0.997, num_simulations=12, seed=9, net="bf16")
+    roots = mcts.run_batch(torch.randn(37, 4), model, train=True)
+    h = roots.host()
+    assert h["error"] == 0 and h["visit_counts"].dtype == np.int32 and h["root_values"].dtype == np.float32
+    np.testing.assert_array_equal(h["visit_counts"], roots.visit_counts.cpu().numpy())
+    np.testing.assert_array_equal(h["root_values"], roots.root_values.cpu().numpy())
+    assert (h["visit_counts"].sum(1) == 12).all()
+    kept = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in h.items()}
+    mcts.run_batch(torch.randn(37, 4), model, train=True).host()          # reuses the arena and the pinned buffer
+    np.testing.assert_array_equal(roots.host()["visit_counts"], kept["visit_counts"])
+    np.testing.assert_array_equal(roots.host()["root_values"], kept["root_values"])
+
+
 def test_launch_counters_and_real_tree_step_hook():
     """smz_stats counts the kernels of the last search and since creation; smz_backup_select runs the fused
     tree step of the captured loop stand-alone and gives the same search as smz_simulate."""
