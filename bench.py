@@ -485,9 +485,15 @@ def main():
         obs4 = torch.randn((B4, shape.obs_dim), generator=torch.Generator().manual_seed(100 + rank)).to(dev)
         b4 = Bench(torch, dist, args, wl4, net, B4, wl4["sims"], world, rank, local, blob, obs4)
         r4 = b4.timed(min(args.steps, 20), 3, flush)
+        rf4 = None
+        if rank == 0:          # roofline of the large-batch network step (the two-tile kernel above one wave of tiles)
+            try:
+                rf4, _ = b4.rooflines(r4["ms_per_step"], r4["mean_leaf_depth"], peaks)
+            except Exception:
+                rf4 = None
         strong = {"workload": wl4["name"], "trees_total": wl4["trees"], "trees_per_gpu": B4, "simulations": wl4["sims"],
                   "value": r4["value"], "unit": UNIT, "ms_per_step": r4["ms_per_step"], "scaling": "strong",
-                  "network_step": net, "weight_broadcast": bcast, "visit_checksum": r4["visit_checksum"]}
+                  "network_step": net, "weight_broadcast": bcast, "visit_checksum": r4["visit_checksum"], "roofline": rf4}
         b4.close()
 
     # ---- the reference's own call, one tree at a time (BASELINE configs[0] shape through the drop-in run()) ----
