@@ -178,7 +178,7 @@ int smz_create(const smz_config* cfg, smz_engine** out) {
   e->cfg.lanes_per_tree = lanes;
 
   const size_t B = a.B, M = a.M;
-  a.row_cap = (a.B + 255) / 256 * 256 + 256;
+  a.row_cap = (a.B + 511) / 512 * 512 + 512;
   a.row_top = a.row_cap;
   const size_t RC = a.row_cap;
   cudaError_t r = cudaSuccess;
@@ -411,7 +411,7 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   count_launches(e, 1);
   CU(cudaGetLastError());
   e->n_trees = n_trees;
-  a.row_top = (n_trees + 255) / 256 * 256 + 256;    // see smz_common.cuh: rows of the two branches never share a tile (pair)
+  a.row_top = (n_trees + 511) / 512 * 512 + 512;    // see smz_common.cuh: rows of the two branches never share a tile (group of 4)
   e->sims_done = 0;
   return SMZ_OK;
 }

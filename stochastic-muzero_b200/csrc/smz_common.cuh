@@ -41,7 +41,7 @@ struct SmzArena {
   // compacted rows of a simulation, double-buffered by simulation parity (the descent of sim s+1 may run in
   // the tail of the kernel that still gathers sim s in another CTA): index smz_row_index(a, sim, branch, row).
   // ONE array of row_top positions per parity: afterstate rows grow upward from 0, dynamics rows downward from
-  // row_top - 1.  row_top = (ceil(trees / 256) + 1) * 256, so a tile of 32 / 64 / 128 / 256 consecutive positions never
+  // row_top - 1.  row_top = (ceil(trees / 512) + 1) * 512, so a tile of 32 / 64 / 128 positions or a group of 2 / 4 tiles never
   // holds rows of both branches and a network CTA can request its positions before the branch counts are known.
   int* rows;        // [2 parities][row_cap] tree ids
   int4* rows4;      // same order: {tree, parent hidden slot, action, 0} — one load per gathered row

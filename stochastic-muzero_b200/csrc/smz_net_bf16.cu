@@ -741,35 +741,41 @@ k_bf16_chain_pipe(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Two tiles per CTA for batches of more than one wave (k_bf16_chain_pipe2).  With one 128-leaf tile per SM the tensor
+// Two or four tiles per CTA for batches of more than one wave (k_bf16_chain_pipeN<2> / <4>).  With one 128-leaf tile per SM the tensor
 // pipe idles while the 16 epilogue warps work through a layer (~1800 cycles, MUFU / issue bound) and the epilogue warps
 // idle while the layer's last K-steps complete (~600 cycles).  A CTA that owns TWO adjacent tiles of the row array (256
 // positions: never both branches, see smz_common.cuh) alternates them: the epilogue warps do (tile 0, layer l), (tile 1,
 // layer l), (tile 0, layer l + 1) ... and the issuer feeds tile 0's layer l + 1 while tile 1's layer l is in the
 // epilogue — the contraction disappears behind the activation function.  Both tiles read the SAME weight tile
-// (one ring, one stream of bulk copies per pair); accumulators: 4 x 128 TMEM columns (tile x parity).
+// (one ring, one stream of bulk copies per group); accumulators: one per tile, NT x 128 TMEM columns.
 // ---------------------------------------------------------------------------------------------
-struct SmemPipe2 {
-  alignas(1024) unsigned char a[2][A_BYTES];
+// NT = tiles per CTA: 2 by default; 4 (cfg4's 516 tiles = 129 quads, one wave instead of two waves of pairs) is kept
+// behind SMZ_PIPE2=4 — it measured slower.  One accumulator per tile is enough (NT x 128 TMEM columns): an epilogue loads all of
+// its tile's accumulator before it hands the first round of columns to the issuer, so the next layer's K-steps never
+// overwrite values that are still to be read.
+template <int NT>
+struct SmemPipeN {
+  alignas(1024) unsigned char a[NT][A_BYTES];
   alignas(1024) unsigned char w[2][W_BYTES];
-  float bias[2][MAXL][TN];
+  float bias[MAXL][TN];            // this CTA's chain, fetched once the branch is known
   unsigned long long wbar[2];
-  unsigned long long dbar[2][2];   // [tile][accumulator parity]
+  unsigned long long dbar[NT];     // accumulator of tile t complete
   unsigned long long bbar;
   unsigned int tmem_base;
-  float4 part[2][4][TM];           // per tile: the head layers of the two tiles follow each other without a barrier between
+  float4 part[2][4][TM];           // head-layer exchange, alternating between consecutive tiles (no barrier between their head layers)
 };
 
+template <int NT>
 __global__ void __launch_bounds__(NPIPE, 1)
-k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
+k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   extern __shared__ unsigned char smem_raw[];
-  SmemPipe2& sm = *reinterpret_cast<SmemPipe2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SmemPipeN<NT>& sm = *reinterpret_cast<SmemPipeN<NT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NR = 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer_warp = warp == NEPI / 32;
   const int r = (warp & 3) * 32 + lane;   // epilogue role: row of a tile == TMEM lane
   const int cb = (warp >> 2) & 3;         // head layers: 32-column block; hidden layers: 16-column slice of a round
-  const int pair = blockIdx.x;            // positions [256 pair, 256 pair + 256) of the row array
+  const int group = blockIdx.x;           // positions [NT * 128 * group, NT * 128 * (group + 1)) of the row array
   const int nl = chain0.n_layers;
 
   auto load_weights = [&](const Chain& c, int l, int slot) {
@@ -779,34 +785,30 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   };
   if (tid == 0) {
     mbar_init(&sm.wbar[0], 1); mbar_init(&sm.wbar[1], 1);
-    mbar_init(&sm.dbar[0][0], 1); mbar_init(&sm.dbar[0][1], 1);
-    mbar_init(&sm.dbar[1][0], 1); mbar_init(&sm.dbar[1][1], 1);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) mbar_init(&sm.dbar[t], 1);
     mbar_init(&sm.bbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const unsigned bbytes = (unsigned)nl * TN * 4;
-    mbar_expect_tx(&sm.bbar, 2 * bbytes);
-    bulk_g2s(sm.bias[0], chain0.bias, bbytes, &sm.bbar);
-    bulk_g2s(sm.bias[1], chain1.bias, bbytes, &sm.bbar);
     load_weights(chain0, 0, 0);              // the first weight tile of BOTH chains: the branch is not known yet
     load_weights(chain1, 0, 1);
   }
   __syncwarp();
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(4 * TN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&sm.tmem_base)), "r"(NT * TN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   smz_pdl_wait();
   smz_pdl_launch_dependents();
   // row records + parent hidden rows of both tiles, requested together with the branch counts
-  int4 rec[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
-  uint4 hrow[2][2];
+  int4 rec[NT];
+  uint4 hrow[NT][2];
 #pragma unroll
-  for (int t = 0; t < 2; ++t) hrow[t][0] = hrow[t][1] = make_uint4(0, 0, 0, 0);
+  for (int t = 0; t < NT; ++t) { rec[t] = make_int4(0, 0, 0, 0); hrow[t][0] = hrow[t][1] = make_uint4(0, 0, 0, 0); }
   if (!is_issuer_warp) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const size_t ri = (size_t)(sim & 1) * a.row_cap + (size_t)(2 * pair + t) * TM + r;
+    for (int t = 0; t < NT; ++t) {
+      const size_t ri = (size_t)(sim & 1) * a.row_cap + (size_t)(NT * group + t) * TM + r;
       rec[t] = a.rows4[ri];
       if (a.xin) {
 #pragma unroll
@@ -822,11 +824,10 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   }
   const int count0 = a.branch_count[sim * 2], count1 = a.branch_count[sim * 2 + 1];
   const int top1 = a.row_top - count1;      // dynamics rows occupy [top1, row_top)
-  const int lo = 2 * pair * TM;
-  const int branch = lo < count0 ? 0 : (lo + 2 * TM > top1 ? 1 : -1);
+  const int lo = NT * group * TM;
+  const int branch = lo < count0 ? 0 : (lo + NT * TM > top1 ? 1 : -1);
   if (branch < 0) {                // nothing to do for this CTA: drain the prefetches, give TMEM back, leave
     if (tid == 0) {
-      mbar_wait(&sm.bbar, 0);
       mbar_wait(&sm.wbar[0], 0);
       mbar_wait(&sm.wbar[1], 0);
     }
@@ -834,13 +835,21 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     __syncthreads();
     tc_fence_after();
     if (warp == 0)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(4 * TN) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(NT * TN) : "memory");
     return;
   }
-  // which of the two tiles carries rows (CTA-uniform): afterstate rows fill the pair from below, dynamics rows from above
-  const bool act0 = branch ? lo + TM > top1 : true;
-  const bool act1 = branch ? true : lo + TM < count0;
+  // which tiles carry rows (CTA-uniform bit mask): afterstate rows fill the group from below, dynamics rows from above
+  unsigned actm = 0;
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+    if (branch ? lo + (t + 1) * TM > top1 : lo + t * TM < count0) actm |= 1u << t;
+  const int t_last = 31 - __clz(actm);      // the tile whose MMAs are issued last in every layer
   const Chain& ch = branch ? chain1 : chain0;
+  if (tid == 0) {                           // this chain's bias table (12 KB), needed by the first epilogue
+    const unsigned bbytes = (unsigned)nl * TN * 4;
+    mbar_expect_tx(&sm.bbar, bbytes);
+    bulk_g2s(sm.bias, ch.bias, bbytes, &sm.bbar);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -867,10 +876,10 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       }
       const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (!(t ? act1 : act0)) continue;
+      for (int t = 0; t < NT; ++t) {
+        if (!((actm >> t) & 1u)) continue;
         const unsigned long long ad = umma_desc(s32(sm.a[t]), CHUNK_A, 128);
-        const unsigned d = tmem + (unsigned)((2 * t + (l & 1)) * TN);
+        const unsigned d = tmem + (unsigned)(t * TN);
         for (int c = 0; c < NR; ++c) {
           nb_sync(2 + 2 * t + c);               // the A columns of round c of tile t are in shared memory
           tc_fence_after();
@@ -883,12 +892,12 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           }
           __syncwarp();
         }
-        if (lane == 0) umma_commit(&sm.dbar[t][l & 1]);
+        if (lane == 0) umma_commit(&sm.dbar[t]);
         __syncwarp();
       }
       if (l + 2 < nl && ((slot ? res1 : res0) != ch.layer[l + 2].w || job.stream_all)) {
-        // the slot is reusable once the MMAs of BOTH tiles have completed (commits complete in issue order)
-        mbar_wait(&sm.dbar[act1 ? 1 : 0][l & 1], (l >> 1) & 1);
+        // the slot is reusable once the MMAs of ALL tiles have completed (commits complete in issue order)
+        mbar_wait(&sm.dbar[t_last], l & 1);
         if (lane == 0) load_weights(ch, l + 2, slot);
         if (slot) { ++nfill1; res1 = ch.layer[l + 2].w; } else { ++nfill0; res0 = ch.layer[l + 2].w; }
         __syncwarp();
@@ -896,13 +905,14 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     }
   } else {
     // =========================== epilogue warps: (tile 0, l), (tile 1, l), (tile 0, l + 1), ... =====================
-    int index[2];
+    int index[NT];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NT; ++t) {
       const int pos = lo + t * TM + r;
-      const bool valid = (t ? act1 : act0) && (branch ? pos >= top1 : pos < count0);
+      const bool tact = (actm >> t) & 1u;
+      const bool valid = tact && (branch ? pos >= top1 : pos < count0);
       index[t] = valid ? rec[t].x : -1;
-      if (t ? act1 : act0) {   // stage the first A operand of tile t
+      if (tact) {              // stage the first A operand of tile t
         const int act = valid ? rec[t].z : -1;
 #pragma unroll
         for (int q = 0; q < 2; ++q) a_store(sm.a[t], r, cb * 2 + q, valid ? hrow[t][q] : make_uint4(0, 0, 0, 0));
@@ -918,21 +928,21 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     }
     fence_async_smem();
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (t ? act1 : act0)
+    for (int t = 0; t < NT; ++t)
+      if ((actm >> t) & 1u)
         for (int c = 0; c < NR; ++c) nb_arrive(2 + 2 * t + c);
     mbar_wait(&sm.bbar, 0);
-    const float (*cbias)[TN] = sm.bias[branch];
+    const float (*cbias)[TN] = sm.bias;
     const int S = job.S;
 
     for (int l = 0; l < nl; ++l) {
       const int kind = ch.layer[l].kind;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (!(t ? act1 : act0)) continue;
+      for (int t = 0; t < NT; ++t) {
+        if (!((actm >> t) & 1u)) continue;
         unsigned char* const A = sm.a[t];
-        const unsigned lane_t = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((2 * t + (l & 1)) * TN);
-        mbar_wait(&sm.dbar[t][l & 1], (l >> 1) & 1);
+        const unsigned lane_t = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(t * TN);
+        mbar_wait(&sm.dbar[t], l & 1);
         __syncwarp();
         tc_fence_after();
         if (kind == LK_HIDDEN) {
@@ -962,7 +972,7 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
           // head layers: row-wise reductions need all columns; warp (quarter, cb) owns the 32-column block cb of its rows
           const int c0 = cb * 32;
           const float* bias = cbias[l] + c0;
-          float4 (*part)[TM] = sm.part[t];
+          float4 (*part)[TM] = sm.part[t & 1];
           uint4 pend[4];
           uint4* pend_dst = nullptr;
           float x[32];
@@ -1036,7 +1046,7 @@ k_bf16_chain_pipe2(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(4 * TN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(NT * TN) : "memory");
   }
 }
 
@@ -1851,7 +1861,7 @@ struct SmzBf16Image {
   int n_sms;
   int timeline_mega;
   int use_pipe;           // K-pipelined chain for the simulation step (SMZ_NO_PIPE=1 turns it off)
-  int use_pipe2;          // two 128-leaf tiles per CTA: -1 = when the tiles exceed one wave of SMs, SMZ_PIPE2=0/1 forces
+  int use_pipe2;          // 128-leaf tiles per CTA: -1 = by batch size (1 / 2 / 4), SMZ_PIPE2 = 0 / 1 (= 2) / 2 / 4 forces
 };
 
 static int round16(int v) { return (v + 15) / 16 * 16; }
@@ -1899,7 +1909,8 @@ int smz_bf16_create(const SmzNetShape& sh, const SmzArena&, SmzBf16Image** out, 
   cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   cudaFuncSetAttribute((const void*)k_bf16_chain_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe) + 1024);
   im->use_pipe = getenv("SMZ_NO_PIPE") ? 0 : 1;
-  cudaFuncSetAttribute((const void*)k_bf16_chain_pipe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipe2) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_pipeN<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipeN<2>) + 1024);
+  cudaFuncSetAttribute((const void*)k_bf16_chain_pipeN<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPipeN<4>) + 1024);
   im->use_pipe2 = getenv("SMZ_PIPE2") ? atoi(getenv("SMZ_PIPE2")) : -1;
   im->use_m64 = getenv("SMZ_M64") ? atoi(getenv("SMZ_M64")) : -1;
   {
@@ -2078,10 +2089,16 @@ void smz_bf16_sim(SmzBf16Image* im, const SmzArena& a, const SmzNetShape& sh, in
                im->chain_dyn, job, sim);
     return;
   }
-  const bool pipe2 = (im->use_pipe2 < 0 ? a.row_top / TM > im->n_sms : im->use_pipe2 != 0) && a.row_top % (2 * TM) == 0;
-  if (tree_mode == 0 && im->use_pipe && pipe2) {
-    smz_launch(k_bf16_chain_pipe2, dim3(a.row_top / (2 * TM)), dim3(NPIPE), sizeof(SmemPipe2) + 1024, s, pdl, a, im->chain_after,
-               im->chain_dyn, job, sim);
+  // tiles per CTA: 1 while the tiles fit one wave of SMs, else 2 (SMZ_PIPE2 = 0 / 1 / 2 / 4 forces).  Four per CTA put cfg4
+  // into ONE wave of 129 CTAs but measured slower than two waves of pairs (65536 trees 5.76 vs 5.16 ms, 32768 trees 4.02 vs 2.50)
+  const int tiles = a.row_top / TM;
+  int nt = im->use_pipe2 < 0 ? (tiles <= im->n_sms ? 1 : 2) : (im->use_pipe2 == 1 ? 2 : im->use_pipe2);
+  if (nt != 2 && nt != 4) nt = 1;
+  if (tree_mode == 0 && im->use_pipe && nt > 1 && a.row_top % (nt * TM) == 0) {
+    if (nt == 2)
+      smz_launch(k_bf16_chain_pipeN<2>, dim3(tiles / 2), dim3(NPIPE), sizeof(SmemPipeN<2>) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
+    else
+      smz_launch(k_bf16_chain_pipeN<4>, dim3(tiles / 4), dim3(NPIPE), sizeof(SmemPipeN<4>) + 1024, s, pdl, a, im->chain_after, im->chain_dyn, job, sim);
     return;
   }
   if (tree_mode == 0 && im->use_pipe) {

@@ -812,7 +812,8 @@ _VARIANTS = {
     "chain_one_thread_issue": {"SMZ_NO_PIPE": "1"},
     "chain_128_rows_2_rounds": {"SMZ_M64": "0"},
     "chain_128_rows_4_rounds": {"SMZ_M64": "0", "SMZ_PIPE_ROUNDS": "4"},
-    "chain_128_rows_two_tiles_per_cta": {"SMZ_M64": "0", "SMZ_PIPE2": "1"},
+    "chain_128_rows_two_tiles_per_cta": {"SMZ_M64": "0", "SMZ_PIPE2": "2"},
+    "chain_128_rows_four_tiles_per_cta": {"SMZ_M64": "0", "SMZ_PIPE2": "4"},
     "chain_64_rows_even_rounds": {"SMZ_M64": "1", "SMZ_M32": "0", "SMZ_M64_EVEN": "1"},
     "chain_64_rows_64_leaves": {"SMZ_M64": "1", "SMZ_M32": "0"},
     "chain_64_rows_32_leaves": {"SMZ_M64": "1", "SMZ_M32": "1"},
