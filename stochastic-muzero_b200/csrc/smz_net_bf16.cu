@@ -763,6 +763,7 @@ struct SmemPipeN {
   unsigned long long bbar;
   unsigned int tmem_base;
   float4 part[2][4][TM];           // head-layer exchange, alternating between consecutive tiles (no barrier between their head layers)
+  int rowidx[NT][TM];              // tree id of every row of every tile (-1 = none)
 };
 
 template <int NT>
@@ -875,7 +876,7 @@ k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
         if (slot) ++nseen1; else ++nseen0;
       }
       const unsigned long long bd = umma_desc(s32(sm.w[slot]), CHUNK_W, 128);
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < NT; ++t) {
         if (!((actm >> t) & 1u)) continue;
         const unsigned long long ad = umma_desc(s32(sm.a[t]), CHUNK_A, 128);
@@ -905,13 +906,12 @@ k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
     }
   } else {
     // =========================== epilogue warps: (tile 0, l), (tile 1, l), (tile 0, l + 1), ... =====================
-    int index[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const int pos = lo + t * TM + r;
       const bool tact = (actm >> t) & 1u;
       const bool valid = tact && (branch ? pos >= top1 : pos < count0);
-      index[t] = valid ? rec[t].x : -1;
+      if (cb == 0) sm.rowidx[t][r] = valid ? rec[t].x : -1;
       if (tact) {              // stage the first A operand of tile t
         const int act = valid ? rec[t].z : -1;
 #pragma unroll
@@ -932,14 +932,16 @@ k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
       if ((actm >> t) & 1u)
         for (int c = 0; c < NR; ++c) nb_arrive(2 + 2 * t + c);
     mbar_wait(&sm.bbar, 0);
+    epi_sync();                              // rowidx is read by other threads from here on
     const float (*cbias)[TN] = sm.bias;
     const int S = job.S;
 
     for (int l = 0; l < nl; ++l) {
       const int kind = ch.layer[l].kind;
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < NT; ++t) {
         if (!((actm >> t) & 1u)) continue;
+        const int index_t = sm.rowidx[t][r];
         unsigned char* const A = sm.a[t];
         const unsigned lane_t = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(t * TN);
         mbar_wait(&sm.dbar[t], l & 1);
@@ -1000,7 +1002,7 @@ k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             const float inv = 1.f / scale;
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = (x[i] - lo_) * inv;
-            if (index[t] >= 0 && job.hidden16_dst) pend_dst = reinterpret_cast<uint4*>(job.hidden16_dst + (size_t)index[t] * SMZ_SP + c0);
+            if (index_t >= 0 && job.hidden16_dst) pend_dst = reinterpret_cast<uint4*>(job.hidden16_dst + (size_t)index_t * SMZ_SP + c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               pend[q] = make_uint4(pack_bf16(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
@@ -1011,7 +1013,7 @@ k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
             const float4 o = part[cb + 1][r];
             const float v = support_scalar(sp, SoftPart{o.x, o.y, o.z});
             float* dst = (kind == LK_PRED) ? job.value_dst : job.reward_dst;
-            if (index[t] >= 0 && dst) dst[index[t]] = v;
+            if (index_t >= 0 && dst) dst[index_t] = v;
           } else if (kind == LK_PRED && cb == 2) {
             const int n = ch.n_policy;
             float m = -1e30f, z = 0.f;
@@ -1022,8 +1024,8 @@ k_bf16_chain_pipeN(SmzArena a, Chain chain0, Chain chain1, Job job, int sim) {
               x[i] = ex2f((x[i] - m) * 1.4426950408889634f);
               z += x[i];
             }
-            if (index[t] >= 0 && job.policy_dst) {
-              float* dst = job.policy_dst + (size_t)index[t] * job.pstride;
+            if (index_t >= 0 && job.policy_dst) {
+              float* dst = job.policy_dst + (size_t)index_t * job.pstride;
               const float inv = 1.f / z;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
