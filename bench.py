@@ -40,7 +40,7 @@ WORKLOADS = {
     "cfg5": dict(name="BASELINE configs[4]: vision ResNet-v2 (98x98 RGB, A 4, S 61, H 126, L 4)", trees=1024, sims=50,
                  dims=dict(action_dim=4, state_dim=61, hidden_dim=126, num_hidden_layers=4), K=2, net="vision"),
 }
-KERNEL_NAMES = {"bf16": "k_bf16_chain_m32 / _m64 / _pipe / _pipe2 by batch size, tcgen05 kind::f16 on bf16 operands",
+KERNEL_NAMES = {"bf16": "k_bf16_chain_m32 / _m64 / _pipe / _pipeN<2> by batch size, tcgen05 kind::f16 on bf16 operands",
                 "f16": "k_tc32_chain_m64<1>, tcgen05 kind::f16 on fp16 operands (one product)",
                 "tc32": "k_tc32_chain_m64, tcgen05 kind::f16 on fp16 hi/lo split operands (hi and lo rows stacked along M: 2 MMAs per K-step give all 4 partial products, fp32-grade)",
                 "fp32": "k_net_sim, fp32 CUDA cores", "vision": "k_vision_step, fp32 CUDA cores"}

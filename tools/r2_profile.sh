@@ -25,7 +25,7 @@ t 300 ncu --set full --clock-control none --cache-control none --import-source o
   python bench.py --net f16 --steps 1 --warmup 3 --profile-only > $O/r2_ncu_c.log 2>&1
 t 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:k_backup_select_sm -s 60 -c 2 -f -o $O/r2_tree_full \
   python bench.py --steps 1 --warmup 3 --profile-only > $O/r2_ncu_d.log 2>&1
-t 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:k_bf16_chain_pipe2 -s 20 -c 2 -f -o $O/r2_pipe2_full \
+t 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:k_bf16_chain_pipeN -s 20 -c 2 -f -o $O/r2_pipe2_full \
   python bench.py --workload cfg4 --steps 1 --warmup 2 --profile-only > $O/r2_ncu_f.log 2>&1
 t 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2_cfg4_launches.csv \
   python bench.py --workload cfg4 --steps 1 --warmup 2 --profile-only > $O/r2_ncu_g.log 2>&1
