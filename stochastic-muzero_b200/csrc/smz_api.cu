@@ -379,9 +379,7 @@ int smz_root(smz_engine* e, int32_t n_trees, const float* obs, const float* root
   cudaStream_t s = (cudaStream_t)stream;
   ON_DEVICE(e);
   SmzArena& a = e->a;
-  CU(cudaMemsetAsync(a.branch_count, 0, (size_t)(a.N + 1) * 2 * sizeof(int), s));
-  CU(cudaMemsetAsync(a.error_flag, 0, sizeof(int), s));
-  CU(cudaMemsetAsync(a.depth_sum, 0, sizeof(unsigned long long), s));
+  smz_launch_begin_search(a, s);       // row counters, error flag, depth statistic
   if (a.dbg) {      // wall-clock stamps: "first" slots start at all-ones (atomicMin), "last" slots at zero (atomicMax)
     std::vector<unsigned long long> init(4 * ((size_t)a.N + 2));
     for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;

@@ -16,6 +16,7 @@ void smz_launch_expand_backup(const SmzArena& a, int lanes, int n_trees, int sim
 void smz_launch_backup_select(const SmzArena& a, int lanes, int n_trees, int sim, bool pdl, cudaStream_t s);
 void smz_launch_read_roots(const SmzArena& a, int n_trees, int* visits, float* values, double* priors, float* rewards,
                            int* error_out, cudaStream_t s);
+void smz_launch_begin_search(const SmzArena& a, cudaStream_t s);
 void smz_launch_set_seed(unsigned long long* dst, unsigned long long seed, unsigned long long tree_id_offset, cudaStream_t s);
 void smz_launch_dirichlet(const SmzArena& a, int n_trees, cudaStream_t s);
 void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperature, const double* u, int* actions,

@@ -377,6 +377,14 @@ void smz_launch_select_actions(const SmzArena& a, int n_trees, double temperatur
   k_select_actions<<<(n_trees + 127) / 128, 128, 0, s>>>(a, n_trees, temperature, u, actions, policy, stored);
 }
 
+// start of a search: the per-simulation row counters, the error flag and the depth statistic in ONE launch (three
+// memsets cost three host enqueues before the first real kernel of a move)
+__global__ void k_begin_search(SmzArena a) {
+  for (int i = threadIdx.x; i < (a.N + 1) * 2; i += blockDim.x) a.branch_count[i] = 0;
+  if (threadIdx.x == 0) { *a.error_flag = 0; *a.depth_sum = 0ull; }
+}
+void smz_launch_begin_search(const SmzArena& a, cudaStream_t s) { k_begin_search<<<1, 128, 0, s>>>(a); }
+
 __global__ void k_set_seed(unsigned long long* dst, unsigned long long seed, unsigned long long tree_id_offset) {
   dst[0] = seed;
   dst[1] = tree_id_offset;

@@ -156,6 +156,12 @@ class SearchEngine:
         self._keep[name] = t
         return t
 
+    def to_device(self, t, dtype):
+        """Host or device tensor / array -> contiguous tensor of `dtype` on the engine's device (asynchronous copy)."""
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.asarray(t))
+        return t.to(device=f"cuda:{self.device}", dtype=dtype, non_blocking=True).contiguous()
+
     @staticmethod
     def _ptr(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None

@@ -398,6 +398,7 @@ class Monte_carlo_tree_search():
                 blob, _ = pack_weights(model)
                 eng.set_weights(blob)
                 self._weights_seen[key] = ver
+        obs = eng.to_device(obs, torch.float32)      # the observations' host-to-device copy is enqueued first
         eng.set_seed(self._next_seed(), self._offset(obs.shape[0]))
         eng.root(obs=obs, root_to_play=root_to_play, train=train)
         eng.simulate(self.num_simulations)
